@@ -1,0 +1,1080 @@
+// C ABI of liberased_cells_b200.so: device context, handles, host-side CellType/CellValue logic and
+// dispatch into the kernel launchers. See include/erased_cells_b200.h for the contract and the
+// reference file:line each entry point replaces.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <vector>
+
+#include "ec_internal.hpp"
+#include "ec_reduce.cuh"
+
+namespace ec {
+
+// ---- thread-local error state --------------------------------------------------------------------
+static thread_local std::string t_error;
+static thread_local uint8_t t_narrow_src = 0, t_narrow_dst = 0;
+static thread_local const char* t_last_kernel = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_error = buf;
+}
+ec_status cuda_fail(cudaError_t e, const char* what) {
+    set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    if (e == cudaErrorMemoryAllocation) return EC_OOM;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) return EC_NO_DEVICE;
+    return EC_CUDA;
+}
+void note_launch(const char* family) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    t_last_kernel = family;
+}
+int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+static ec_status narrowing(uint8_t src, uint8_t dst) {
+    t_narrow_src = src;
+    t_narrow_dst = dst;
+    set_error("Invalid narrowing from cell-type %s to %s", ec_ctype_name(src), ec_ctype_name(dst));  // src/error.rs:14
+    return EC_NARROWING;
+}
+static ec_status invalid(const char* what) {
+    set_error("invalid argument: %s", what);
+    return EC_INVALID_ARG;
+}
+
+// ---- device context --------------------------------------------------------------------------------
+struct Ctx {
+    std::mutex mu;
+    bool inited = false;
+    int device = -1;
+    cudaStream_t own = nullptr;
+    cudaDeviceProp prop;
+    int max_grid = 0;
+};
+static Ctx g_ctx;
+static thread_local cudaStream_t t_stream = nullptr;
+static thread_local bool t_stream_set = false;
+static thread_local bool t_device_bound = false;
+
+struct ThreadScratch {
+    std::vector<std::pair<cudaStream_t, ReduceScratch>> per_stream;
+    uint64_t* pinned = nullptr;  // 8 words of pinned host staging for scalar results
+};
+static thread_local ThreadScratch t_scratch;
+constexpr size_t kMaxReduceBlocks = 8192;
+
+static ec_status ensure() {
+    if (!g_ctx.inited) {
+        const int dev = env_int("EC_DEVICE", env_int("LOCAL_RANK", 0));
+        if (ec_status s = ec_init(dev)) return s;
+    }
+    if (!t_device_bound) {
+        if (cudaError_t e = cudaSetDevice(g_ctx.device)) return cuda_fail(e, "cudaSetDevice");
+        t_device_bound = true;
+    }
+    return EC_OK;
+}
+static cudaStream_t cur_stream() { return t_stream_set ? t_stream : g_ctx.own; }
+static Launch launch_ctx() { return Launch{cur_stream(), g_ctx.prop.multiProcessorCount, g_ctx.max_grid}; }
+
+static ec_status dev_alloc(void** p, size_t bytes) {
+    *p = nullptr;
+    if (bytes == 0) return EC_OK;
+    bytes = (bytes + 255) & ~size_t(255);
+    if (cudaError_t e = cudaMallocAsync(p, bytes, cur_stream())) return cuda_fail(e, "cudaMallocAsync");
+    return EC_OK;
+}
+static void dev_free(void* p) {
+    if (p) cudaFreeAsync(p, cur_stream());
+}
+static ec_status sync_stream() {
+    if (cudaError_t e = cudaStreamSynchronize(cur_stream())) return cuda_fail(e, "cudaStreamSynchronize");
+    return EC_OK;
+}
+static ec_status pinned_words(uint64_t** out) {
+    if (!t_scratch.pinned) {
+        if (cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&t_scratch.pinned), 64)) return cuda_fail(e, "cudaMallocHost");
+    }
+    *out = t_scratch.pinned;
+    return EC_OK;
+}
+static ec_status reduce_scratch(ReduceScratch* out) {
+    const cudaStream_t s = cur_stream();
+    for (auto& kv : t_scratch.per_stream)
+        if (kv.first == s) { *out = kv.second; return EC_OK; }
+    ReduceScratch sc;
+    void* base = nullptr;
+    const size_t bytes = (2 * kMaxReduceBlocks + 4 + 2) * sizeof(uint64_t);
+    if (cudaError_t e = cudaMalloc(&base, bytes)) return cuda_fail(e, "cudaMalloc(reduce scratch)");
+    if (cudaError_t e = cudaMemset(base, 0, bytes)) return cuda_fail(e, "cudaMemset(reduce scratch)");
+    sc.partials = static_cast<uint64_t*>(base);
+    sc.result = sc.partials + 2 * kMaxReduceBlocks;
+    sc.ticket = reinterpret_cast<unsigned int*>(sc.result + 4);
+    t_scratch.per_stream.emplace_back(s, sc);
+    *out = sc;
+    return EC_OK;
+}
+
+// ---- host-side CellType lattice — src/ctype.rs ------------------------------------------------------
+static const size_t kSize[10] = {1, 2, 4, 8, 1, 2, 4, 8, 4, 8};
+static const char* const kName[10] = {"UInt8", "UInt16", "UInt32", "UInt64", "Int8", "Int16", "Int32", "Int64", "Float32", "Float64"};
+static inline bool ct_ok(unsigned ct) { return ct < 10; }
+static inline bool ct_integral(uint8_t ct) { return ct < EC_FLOAT32; }
+static inline bool ct_signed(uint8_t ct) { return ct >= EC_INT8; }
+
+// src/ctype.rs:99-126: smallest type holding both; anything not representable is Float64
+static uint8_t ct_union(uint8_t a, uint8_t b) {
+    const bool ai = ct_integral(a), bi = ct_integral(b), as = ct_signed(a), bs = ct_signed(b);
+    const size_t sa = kSize[a], sb = kSize[b];
+    size_t need;
+    if (ai != bi) need = ai ? std::max(sb, 2 * sa) : std::max(sa, 2 * sb);          // int with float
+    else if (as != bs) need = as ? std::max(sa, 2 * sb) : std::max(sb, 2 * sa);      // signed with unsigned
+    else need = std::max(sa, sb);
+    const bool sg = as || bs, in = ai && bi;
+    if (in) {
+        switch (need) {
+            case 1: return sg ? EC_INT8 : EC_UINT8;
+            case 2: return sg ? EC_INT16 : EC_UINT16;
+            case 4: return sg ? EC_INT32 : EC_UINT32;
+            case 8: return sg ? EC_INT64 : EC_UINT64;
+        }
+        return EC_FLOAT64;
+    }
+    return need == 4 ? EC_FLOAT32 : EC_FLOAT64;
+}
+static inline bool ct_fits(uint8_t s, uint8_t d) { return ct_union(s, d) == d; }
+
+// ---- host-side CellValue — src/value.rs --------------------------------------------------------------
+template <class T> static inline T payload(const ec_value& v) {
+    T x;
+    memcpy(&x, &v.bits, sizeof(T));
+    return x;
+}
+template <class T> static inline ec_value tagged(uint8_t ct, T x) {
+    ec_value v;
+    memset(&v, 0, sizeof v);
+    v.ct = ct;
+    memcpy(&v.bits, &x, sizeof(T));
+    return v;
+}
+struct Widened {  // a cell widened the way ToPrimitive sees it
+    bool is_float, is_neg_int;
+    double f;
+    uint64_t u;  // magnitude-preserving two's complement for ints
+    int64_t i;
+};
+static Widened widen(const ec_value& v) {
+    Widened w{};
+    switch (v.ct) {
+        case EC_UINT8: w.u = payload<uint8_t>(v); w.i = (int64_t)w.u; break;
+        case EC_UINT16: w.u = payload<uint16_t>(v); w.i = (int64_t)w.u; break;
+        case EC_UINT32: w.u = payload<uint32_t>(v); w.i = (int64_t)w.u; break;
+        case EC_UINT64: w.u = payload<uint64_t>(v); w.i = (int64_t)w.u; break;
+        case EC_INT8: w.i = payload<int8_t>(v); w.u = (uint64_t)w.i; break;
+        case EC_INT16: w.i = payload<int16_t>(v); w.u = (uint64_t)w.i; break;
+        case EC_INT32: w.i = payload<int32_t>(v); w.u = (uint64_t)w.i; break;
+        case EC_INT64: w.i = payload<int64_t>(v); w.u = (uint64_t)w.i; break;
+        case EC_FLOAT32: w.is_float = true; w.f = (double)payload<float>(v); break;  // cvtss2sd
+        default: w.is_float = true; w.f = payload<double>(v); break;
+    }
+    w.is_neg_int = !w.is_float && ct_signed(v.ct) && w.i < 0;
+    return w;
+}
+// `as f64` (src/value.rs:144-156)
+static double value_as_f64(const ec_value& v) {
+    const Widened w = widen(v);
+    if (w.is_float) return w.f;
+    return ct_signed(v.ct) ? (double)w.i : (double)w.u;
+}
+// the four ops as the SSE2 instructions of the reference's platform, operand order pinned
+static double host_f64_op(int op, double a, double b) {
+#if defined(__x86_64__)
+    switch (op) {
+        case EC_ADD: __asm__("addsd %1, %0" : "+x"(a) : "x"(b)); break;
+        case EC_SUB: __asm__("subsd %1, %0" : "+x"(a) : "x"(b)); break;
+        case EC_MUL: __asm__("mulsd %1, %0" : "+x"(a) : "x"(b)); break;
+        default: __asm__("divsd %1, %0" : "+x"(a) : "x"(b)); break;
+    }
+    return a;
+#else
+    double r = op == EC_ADD ? a + b : op == EC_SUB ? a - b : op == EC_MUL ? a * b : a / b;
+    if (r != r) {  // same rule the kernels apply
+        uint64_t ab, bb, o = 0xFFF8000000000000ull;
+        memcpy(&ab, &a, 8); memcpy(&bb, &b, 8);
+        if (b != b) o = bb | 0x0008000000000000ull;
+        if (a != a) o = ab | 0x0008000000000000ull;
+        memcpy(&r, &o, 8);
+    }
+    return r;
+#endif
+}
+// legal widening of a scalar (src/value.rs:74-98); caller has checked ct_fits
+static ec_value value_widen(const ec_value& v, uint8_t dst) {
+    if (dst == v.ct) return v;
+    const Widened w = widen(v);
+    switch (dst) {
+        case EC_FLOAT64: return tagged<double>(dst, value_as_f64(v));
+        case EC_FLOAT32: return tagged<float>(dst, w.is_float ? (float)w.f : (float)w.i);  // 8/16-bit ints: exact
+        case EC_UINT16: return tagged<uint16_t>(dst, (uint16_t)w.u);
+        case EC_UINT32: return tagged<uint32_t>(dst, (uint32_t)w.u);
+        case EC_UINT64: return tagged<uint64_t>(dst, w.u);
+        case EC_INT16: return tagged<int16_t>(dst, (int16_t)w.i);
+        case EC_INT32: return tagged<int32_t>(dst, (int32_t)w.i);
+        case EC_INT64: return tagged<int64_t>(dst, w.i);
+    }
+    return v;
+}
+static int cmp3u(uint64_t a, uint64_t b) { return a < b ? -1 : (a > b ? 1 : 0); }
+static int cmp3i(int64_t a, int64_t b) { return a < b ? -1 : (a > b ? 1 : 0); }
+// total-order key of a float payload
+static int64_t total_key64(double d) {
+    int64_t b;
+    memcpy(&b, &d, 8);
+    return b ^ (int64_t)((uint64_t)(b >> 63) >> 1);
+}
+static int32_t total_key32(float f) {
+    int32_t b;
+    memcpy(&b, &f, 4);
+    return b ^ (int32_t)((uint32_t)(b >> 31) >> 1);
+}
+// src/value.rs:248-265
+static int value_cmp(const ec_value& l, const ec_value& r) {
+    const uint8_t u = ct_union(l.ct, r.ct);
+    const ec_value a = value_widen(l, u), b = value_widen(r, u);
+    switch (u) {
+        case EC_FLOAT32: return cmp3i(total_key32(payload<float>(a)), total_key32(payload<float>(b)));
+        case EC_FLOAT64: return cmp3i(total_key64(payload<double>(a)), total_key64(payload<double>(b)));
+        default: return ct_signed(u) ? cmp3i(widen(a).i, widen(b).i) : cmp3u(widen(a).u, widen(b).u);
+    }
+}
+static ec_value value_min(uint8_t ct) {
+    switch (ct) {
+        case EC_INT8: return tagged<int8_t>(ct, std::numeric_limits<int8_t>::min());
+        case EC_INT16: return tagged<int16_t>(ct, std::numeric_limits<int16_t>::min());
+        case EC_INT32: return tagged<int32_t>(ct, std::numeric_limits<int32_t>::min());
+        case EC_INT64: return tagged<int64_t>(ct, std::numeric_limits<int64_t>::min());
+        case EC_FLOAT32: return tagged<float>(ct, std::numeric_limits<float>::lowest());
+        case EC_FLOAT64: return tagged<double>(ct, std::numeric_limits<double>::lowest());
+        default: return tagged<uint64_t>(ct, 0);
+    }
+}
+static ec_value value_max(uint8_t ct) {
+    switch (ct) {
+        case EC_UINT8: return tagged<uint8_t>(ct, 0xFF);
+        case EC_UINT16: return tagged<uint16_t>(ct, 0xFFFF);
+        case EC_UINT32: return tagged<uint32_t>(ct, 0xFFFFFFFFu);
+        case EC_UINT64: return tagged<uint64_t>(ct, ~0ull);
+        case EC_INT8: return tagged<int8_t>(ct, std::numeric_limits<int8_t>::max());
+        case EC_INT16: return tagged<int16_t>(ct, std::numeric_limits<int16_t>::max());
+        case EC_INT32: return tagged<int32_t>(ct, std::numeric_limits<int32_t>::max());
+        case EC_INT64: return tagged<int64_t>(ct, std::numeric_limits<int64_t>::max());
+        case EC_FLOAT32: return tagged<float>(ct, std::numeric_limits<float>::max());
+        default: return tagged<double>(ct, std::numeric_limits<double>::max());
+    }
+}
+static ec_value value_of_int(uint8_t ct, int x) {  // zero()/one()
+    switch (ct) {
+        case EC_FLOAT32: return tagged<float>(ct, (float)x);
+        case EC_FLOAT64: return tagged<double>(ct, (double)x);
+        default: return tagged<uint64_t>(ct, (uint64_t)x);
+    }
+}
+// NoData::value — src/masked/nodata.rs:23-40
+static bool nodata_sentinel(int kind, uint8_t ct, const ec_value* v, ec_value* out) {
+    if (kind == EC_NODATA_NONE) return false;
+    if (kind == EC_NODATA_VALUE) { *out = *v; return true; }
+    if (ct == EC_FLOAT32) *out = tagged<uint32_t>(ct, 0x7FC00000u);                 // f32::NAN
+    else if (ct == EC_FLOAT64) *out = tagged<uint64_t>(ct, 0x7FF8000000000000ull);  // f64::NAN
+    else *out = value_min(ct);
+    return true;
+}
+
+// ---- handles -----------------------------------------------------------------------------------------
+static ec_status new_buf(uint8_t ct, size_t len, ec_buf** out) {
+    ec_buf* b = new ec_buf{ct, true, len, 0, nullptr};
+    b->capacity_bytes = len * kSize[ct];
+    if (ec_status s = dev_alloc(&b->dptr, b->capacity_bytes)) { delete b; return s; }
+    *out = b;
+    return EC_OK;
+}
+static size_t mask_bytes(size_t len) { return (((len + 31) / 32) * 4 + 15) & ~size_t(15); }
+static ec_status new_mask(size_t len, ec_mask** out) {
+    ec_mask* m = new ec_mask{len, mask_bytes(len), nullptr};
+    void* p = nullptr;
+    if (ec_status s = dev_alloc(&p, m->capacity_bytes)) { delete m; return s; }
+    m->words = static_cast<uint32_t*>(p);
+    *out = m;
+    return EC_OK;
+}
+#define EC_TRY(expr) do { if (ec_status _s = (expr)) return _s; } while (0)
+#define EC_CUDA_TRY(expr, what) do { if (cudaError_t _e = (expr)) return cuda_fail(_e, what); } while (0)
+#define EC_LAUNCH(expr, family) do { if (cudaError_t _e = (expr)) return cuda_fail(_e, family); note_launch(family); } while (0)
+
+// per-left-type launchers generated by ec_tu_binary.cu
+#define DECL(n)                                                                                                          \
+    cudaError_t launch_binary_l##n(const Launch&, int, const void*, int, const void*, double*, size_t, const uint32_t*, \
+                                   const uint32_t*, uint32_t*);                                                         \
+    cudaError_t launch_normdiff_l##n(const Launch&, const void*, int, const void*, double*, size_t);                    \
+    cudaError_t launch_binary_scalar_l##n(const Launch&, int, const void*, int, const void*, int, double, double*, size_t);
+DECL(0) DECL(1) DECL(2) DECL(3) DECL(4) DECL(5) DECL(6) DECL(7) DECL(8) DECL(9)
+#undef DECL
+using BinFn = cudaError_t (*)(const Launch&, int, const void*, int, const void*, double*, size_t, const uint32_t*, const uint32_t*, uint32_t*);
+using NdFn = cudaError_t (*)(const Launch&, const void*, int, const void*, double*, size_t);
+using BsFn = cudaError_t (*)(const Launch&, int, const void*, int, const void*, int, double, double*, size_t);
+static const BinFn kBinary[10] = {launch_binary_l0, launch_binary_l1, launch_binary_l2, launch_binary_l3, launch_binary_l4,
+                                  launch_binary_l5, launch_binary_l6, launch_binary_l7, launch_binary_l8, launch_binary_l9};
+static const NdFn kNormDiff[10] = {launch_normdiff_l0, launch_normdiff_l1, launch_normdiff_l2, launch_normdiff_l3, launch_normdiff_l4,
+                                   launch_normdiff_l5, launch_normdiff_l6, launch_normdiff_l7, launch_normdiff_l8, launch_normdiff_l9};
+static const BsFn kBinScalar[10] = {launch_binary_scalar_l0, launch_binary_scalar_l1, launch_binary_scalar_l2, launch_binary_scalar_l3,
+                                    launch_binary_scalar_l4, launch_binary_scalar_l5, launch_binary_scalar_l6, launch_binary_scalar_l7,
+                                    launch_binary_scalar_l8, launch_binary_scalar_l9};
+
+cudaError_t launch_binary(const Launch& L, int op, int lct, const void* l, int rct, const void* r, double* out, size_t n,
+                          const uint32_t* lm, const uint32_t* rm, uint32_t* om) {
+    return kBinary[lct](L, op, l, rct, r, out, n, lm, rm, om);
+}
+cudaError_t launch_normdiff(const Launch& L, int lct, const void* l, int rct, const void* r, double* out, size_t n) {
+    return kNormDiff[lct](L, l, rct, r, out, n);
+}
+cudaError_t launch_binary_scalar(const Launch& L, int op1, int lct, const void* l, int rct, const void* r, int op2, double s,
+                                 double* out, size_t n) {
+    return kBinScalar[lct](L, op1, l, rct, r, op2, s, out, n);
+}
+
+// reduce a buffer to {min_key, max_key} (device, in scratch.result)
+static ec_status run_min_max(const ec_buf* b, const ec_mask* m, ReduceScratch* sc) {
+    EC_TRY(reduce_scratch(sc));
+    EC_LAUNCH(launch_min_max(launch_ctx(), b->ct, b->dptr, m ? m->words : nullptr, b->len, *sc), "min_max");
+    return EC_OK;
+}
+
+}  // namespace ec
+
+using namespace ec;
+
+extern "C" {
+
+// ---- library / device context ------------------------------------------------------------------------
+int ec_abi_version(void) { return EC_ABI_VERSION; }
+const char* ec_last_error(void) { return t_error.c_str(); }
+void ec_last_narrowing(uint8_t* src, uint8_t* dst) {
+    if (src) *src = t_narrow_src;
+    if (dst) *dst = t_narrow_dst;
+}
+ec_status ec_init(int device) {
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    if (g_ctx.inited) {
+        if (device != g_ctx.device) return invalid("ec_init: this process is already bound to another device");
+        return EC_OK;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("no usable CUDA device (%s); erased_cells_b200 has no CPU path", e ? cudaGetErrorString(e) : "0 devices");
+        return EC_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) return invalid("ec_init: device index out of range");
+    EC_CUDA_TRY(cudaSetDevice(device), "cudaSetDevice");
+    EC_CUDA_TRY(cudaGetDeviceProperties(&g_ctx.prop, device), "cudaGetDeviceProperties");
+    EC_CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.own, cudaStreamNonBlocking), "cudaStreamCreate");
+    // stream-ordered pool that keeps freed blocks: output allocation stays off the critical path
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    g_ctx.max_grid = env_int("EC_MAX_GRID", 0);
+    g_ctx.device = device;
+    g_ctx.inited = true;
+    t_device_bound = true;
+    return EC_OK;
+}
+ec_status ec_device_info_get(ec_device_info* out) {
+    EC_TRY(ensure());
+    memset(out, 0, sizeof *out);
+    out->device = g_ctx.device;
+    out->sm_count = g_ctx.prop.multiProcessorCount;
+    out->cc_major = g_ctx.prop.major;
+    out->cc_minor = g_ctx.prop.minor;
+    out->l2_bytes = g_ctx.prop.l2CacheSize;
+    out->total_mem_bytes = g_ctx.prop.totalGlobalMem;
+    strncpy(out->name, g_ctx.prop.name, sizeof(out->name) - 1);
+    return EC_OK;
+}
+ec_status ec_set_stream(void* cuda_stream) {
+    EC_TRY(ensure());
+    t_stream = static_cast<cudaStream_t>(cuda_stream);
+    t_stream_set = cuda_stream != nullptr;
+    return EC_OK;
+}
+void* ec_get_stream(void) { return ensure() == EC_OK ? cur_stream() : nullptr; }
+ec_status ec_synchronize(void) {
+    EC_TRY(ensure());
+    return sync_stream();
+}
+uint64_t ec_kernel_launches(void) { return g_launches.load(); }
+const char* ec_last_kernel(void) { return t_last_kernel; }
+ec_status ec_event_create(ec_event** out) {
+    EC_TRY(ensure());
+    ec_event* e = new ec_event{};
+    if (cudaError_t err = cudaEventCreate(&e->ev)) { delete e; return cuda_fail(err, "cudaEventCreate"); }
+    *out = e;
+    return EC_OK;
+}
+ec_status ec_event_record(ec_event* e) {
+    EC_TRY(ensure());
+    EC_CUDA_TRY(cudaEventRecord(e->ev, cur_stream()), "cudaEventRecord");
+    return EC_OK;
+}
+ec_status ec_event_elapsed_ms(ec_event* a, ec_event* b, float* ms) {
+    EC_CUDA_TRY(cudaEventSynchronize(b->ev), "cudaEventSynchronize");
+    EC_CUDA_TRY(cudaEventElapsedTime(ms, a->ev, b->ev), "cudaEventElapsedTime");
+    return EC_OK;
+}
+void ec_event_destroy(ec_event* e) {
+    if (e) { cudaEventDestroy(e->ev); delete e; }
+}
+ec_status ec_host_alloc(size_t bytes, void** out) {
+    EC_TRY(ensure());
+    if (cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1)) { cuda_fail(e, "cudaMallocHost"); return EC_OOM; }
+    return EC_OK;
+}
+void ec_host_free(void* p) { if (p) cudaFreeHost(p); }
+ec_status ec_host_register(void* p, size_t bytes) {
+    EC_TRY(ensure());
+    EC_CUDA_TRY(cudaHostRegister(p, bytes, cudaHostRegisterDefault), "cudaHostRegister");
+    return EC_OK;
+}
+ec_status ec_host_unregister(void* p) {
+    EC_CUDA_TRY(cudaHostUnregister(p), "cudaHostUnregister");
+    return EC_OK;
+}
+
+// ---- CellType ----------------------------------------------------------------------------------------
+uint8_t ec_ctype_union(uint8_t a, uint8_t b) { return (ct_ok(a) && ct_ok(b)) ? ct_union(a, b) : EC_FLOAT64; }
+int ec_ctype_can_fit_into(uint8_t a, uint8_t b) { return ct_ok(a) && ct_ok(b) && ct_fits(a, b); }
+size_t ec_ctype_size_of(uint8_t ct) { return ct_ok(ct) ? kSize[ct] : 0; }
+int ec_ctype_is_integral(uint8_t ct) { return ct_ok(ct) && ct_integral(ct); }
+int ec_ctype_is_signed(uint8_t ct) { return ct_ok(ct) && ct_signed(ct); }
+const char* ec_ctype_name(uint8_t ct) { return ct_ok(ct) ? kName[ct] : "?"; }
+ec_status ec_ctype_from_name(const char* s, uint8_t* out) {
+    for (uint8_t i = 0; i < 10; ++i)
+        if (strcmp(s, kName[i]) == 0) { *out = i; return EC_OK; }
+    set_error("Unable to parse %s as a CellType", s);  // src/error.rs:20-21
+    return EC_PARSE;
+}
+ec_status ec_ctype_min_value(uint8_t ct, ec_value* out) { if (!ct_ok(ct)) return invalid("cell type"); *out = value_min(ct); return EC_OK; }
+ec_status ec_ctype_max_value(uint8_t ct, ec_value* out) { if (!ct_ok(ct)) return invalid("cell type"); *out = value_max(ct); return EC_OK; }
+ec_status ec_ctype_zero(uint8_t ct, ec_value* out) { if (!ct_ok(ct)) return invalid("cell type"); *out = value_of_int(ct, 0); return EC_OK; }
+ec_status ec_ctype_one(uint8_t ct, ec_value* out) { if (!ct_ok(ct)) return invalid("cell type"); *out = value_of_int(ct, 1); return EC_OK; }
+
+// ---- CellValue ---------------------------------------------------------------------------------------
+ec_status ec_value_convert(const ec_value* v, uint8_t ct, ec_value* out) {
+    if (!ct_ok(v->ct) || !ct_ok(ct)) return invalid("cell type");
+    if (!ct_fits(v->ct, ct)) return narrowing(v->ct, ct);
+    *out = value_widen(*v, ct);
+    return EC_OK;
+}
+ec_status ec_value_binary(int op, const ec_value* l, const ec_value* r, ec_value* out) {
+    if (!ct_ok(l->ct) || !ct_ok(r->ct) || op < 0 || op > 3) return invalid("cell type / op");
+    // unify (src/value.rs:103-107) is value-exact for every pair, so `as f64` of the operands is the
+    // same number the reference feeds to the f64 op
+    const uint8_t u = ct_union(l->ct, r->ct);
+    *out = tagged<double>(EC_FLOAT64, host_f64_op(op, value_as_f64(value_widen(*l, u)), value_as_f64(value_widen(*r, u))));
+    return EC_OK;
+}
+ec_status ec_value_neg(const ec_value* v, ec_value* out) {
+    if (!ct_ok(v->ct)) return invalid("cell type");
+    const Widened w = widen(*v);
+    switch (v->ct) {
+        case EC_UINT8: *out = tagged<int16_t>(EC_INT16, (int16_t)(-(int)w.u)); break;
+        case EC_UINT16: *out = tagged<int32_t>(EC_INT32, -(int32_t)w.u); break;
+        case EC_UINT32: case EC_UINT64: {
+            uint64_t b; const double d = (double)w.u; memcpy(&b, &d, 8);
+            *out = tagged<uint64_t>(EC_FLOAT64, b ^ 0x8000000000000000ull);
+            break;
+        }
+        case EC_INT8: *out = tagged<int8_t>(v->ct, (int8_t)(0u - (uint8_t)w.i)); break;
+        case EC_INT16: *out = tagged<int16_t>(v->ct, (int16_t)(0u - (uint16_t)w.i)); break;
+        case EC_INT32: *out = tagged<int32_t>(v->ct, (int32_t)(0u - (uint32_t)w.i)); break;
+        case EC_INT64: *out = tagged<int64_t>(v->ct, (int64_t)(0ull - (uint64_t)w.i)); break;
+        case EC_FLOAT32: *out = tagged<uint32_t>(v->ct, payload<uint32_t>(*v) ^ 0x80000000u); break;
+        default: *out = tagged<uint64_t>(v->ct, v->bits ^ 0x8000000000000000ull); break;
+    }
+    return EC_OK;
+}
+ec_status ec_value_cmp(const ec_value* l, const ec_value* r, int* ordering) {
+    if (!ct_ok(l->ct) || !ct_ok(r->ct)) return invalid("cell type");
+    *ordering = value_cmp(*l, *r);
+    return EC_OK;
+}
+ec_status ec_value_to_f64(const ec_value* v, double* out, int* is_some) {
+    if (!ct_ok(v->ct)) return invalid("cell type");
+    *out = value_as_f64(*v);
+    *is_some = 1;
+    return EC_OK;
+}
+// num-traits 0.2.17 float->int: Some(trunc) iff inside the representable open interval
+ec_status ec_value_to_i64(const ec_value* v, int64_t* out, int* is_some) {
+    if (!ct_ok(v->ct)) return invalid("cell type");
+    const Widened w = widen(*v);
+    if (w.is_float) {
+        *is_some = (w.f >= -9223372036854775808.0 && w.f < 9223372036854775808.0);
+        *out = *is_some ? (int64_t)w.f : 0;
+    } else if (v->ct == EC_UINT64) {
+        *is_some = w.u <= (uint64_t)std::numeric_limits<int64_t>::max();
+        *out = *is_some ? (int64_t)w.u : 0;
+    } else { *is_some = 1; *out = w.i; }
+    return EC_OK;
+}
+ec_status ec_value_to_u64(const ec_value* v, uint64_t* out, int* is_some) {
+    if (!ct_ok(v->ct)) return invalid("cell type");
+    const Widened w = widen(*v);
+    if (w.is_float) {
+        *is_some = (w.f > -1.0 && w.f < 18446744073709551616.0);
+        *out = *is_some ? (uint64_t)w.f : 0;
+    } else { *is_some = !w.is_neg_int; *out = *is_some ? w.u : 0; }
+    return EC_OK;
+}
+
+// ---- CellBuffer --------------------------------------------------------------------------------------
+ec_status ec_buf_from_host(uint8_t ct, const void* host, size_t len, ec_buf** out) {
+    EC_TRY(ensure());
+    if (!ct_ok(ct)) return invalid("cell type");
+    ec_buf* b;
+    EC_TRY(new_buf(ct, len, &b));
+    if (len) {
+        if (cudaError_t e = cudaMemcpyAsync(b->dptr, host, len * kSize[ct], cudaMemcpyHostToDevice, cur_stream())) {
+            ec_buf_free(b);
+            return cuda_fail(e, "cudaMemcpyAsync(H2D)");
+        }
+    }
+    *out = b;
+    return EC_OK;
+}
+ec_status ec_buf_with_defaults(size_t len, uint8_t ct, ec_buf** out) {
+    EC_TRY(ensure());
+    if (!ct_ok(ct)) return invalid("cell type");
+    ec_buf* b;
+    EC_TRY(new_buf(ct, len, &b));
+    if (len) EC_CUDA_TRY(cudaMemsetAsync(b->dptr, 0, len * kSize[ct], cur_stream()), "cudaMemsetAsync");
+    *out = b;
+    return EC_OK;
+}
+ec_status ec_buf_fill(size_t len, const ec_value* value, ec_buf** out) {
+    EC_TRY(ensure());
+    if (!ct_ok(value->ct)) return invalid("cell type");
+    ec_buf* b;
+    EC_TRY(new_buf(value->ct, len, &b));
+    if (len) EC_LAUNCH(launch_fill(launch_ctx(), b->ct, b->dptr, len, value->bits), "fill");
+    *out = b;
+    return EC_OK;
+}
+ec_status ec_buf_wrap_device(uint8_t ct, void* device_ptr, size_t len, ec_buf** out) {
+    EC_TRY(ensure());
+    if (!ct_ok(ct)) return invalid("cell type");
+    if (reinterpret_cast<uintptr_t>(device_ptr) % 32 != 0) return invalid("device pointer must be 32-byte aligned (row strips start on 128-cell boundaries)");
+    *out = new ec_buf{ct, false, len, len * kSize[ct], device_ptr};
+    return EC_OK;
+}
+ec_status ec_buf_clone(const ec_buf* b, ec_buf** out) {
+    EC_TRY(ensure());
+    ec_buf* c;
+    EC_TRY(new_buf(b->ct, b->len, &c));
+    if (b->len) EC_CUDA_TRY(cudaMemcpyAsync(c->dptr, b->dptr, b->len * kSize[b->ct], cudaMemcpyDeviceToDevice, cur_stream()), "cudaMemcpyAsync(D2D)");
+    *out = c;
+    return EC_OK;
+}
+void ec_buf_free(ec_buf* b) {
+    if (!b) return;
+    if (b->owned) dev_free(b->dptr);
+    delete b;
+}
+size_t ec_buf_len(const ec_buf* b) { return b->len; }
+uint8_t ec_buf_ctype(const ec_buf* b) { return b->ct; }
+void* ec_buf_device_ptr(const ec_buf* b) { return b->dptr; }
+ec_status ec_buf_to_host(const ec_buf* b, void* host, size_t host_bytes) {
+    EC_TRY(ensure());
+    const size_t bytes = b->len * kSize[b->ct];
+    if (host_bytes < bytes) return invalid("ec_buf_to_host: host buffer too small");
+    if (bytes) EC_CUDA_TRY(cudaMemcpyAsync(host, b->dptr, bytes, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
+    return sync_stream();
+}
+ec_status ec_buf_get(const ec_buf* b, size_t index, ec_value* out) {
+    EC_TRY(ensure());
+    if (index >= b->len) { set_error("index out of bounds: the len is %zu but the index is %zu", b->len, index); return EC_OOB; }
+    uint64_t* pin;
+    EC_TRY(pinned_words(&pin));
+    pin[0] = 0;
+    EC_CUDA_TRY(cudaMemcpyAsync(pin, static_cast<const char*>(b->dptr) + index * kSize[b->ct], kSize[b->ct], cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
+    EC_TRY(sync_stream());
+    *out = tagged<uint64_t>(b->ct, pin[0]);
+    return EC_OK;
+}
+ec_status ec_buf_put(ec_buf* b, size_t index, const ec_value* value) {
+    EC_TRY(ensure());
+    if (!ct_ok(value->ct)) return invalid("cell type");
+    if (!ct_fits(value->ct, b->ct)) return narrowing(value->ct, b->ct);  // convert()? happens before the index (src/buffer.rs:137)
+    if (index >= b->len) { set_error("index out of bounds: the len is %zu but the index is %zu", b->len, index); return EC_OOB; }
+    const ec_value c = value_widen(*value, b->ct);
+    uint64_t* pin;
+    EC_TRY(pinned_words(&pin));
+    pin[1] = c.bits;
+    EC_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(b->dptr) + index * kSize[b->ct], &pin[1], kSize[b->ct], cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
+    return sync_stream();
+}
+ec_status ec_buf_extend_host(ec_buf* b, uint8_t ct, const void* host, size_t n) {
+    EC_TRY(ensure());
+    if (!ct_ok(ct)) return invalid("cell type");
+    if (!b->owned) return invalid("cannot extend a wrapped buffer");
+    // `to_<p>().unwrap()` (src/buffer.rs:212) cannot fail for a legal widening; the remaining pairs
+    // would need a value-dependent range check and are refused like a narrowing convert.
+    if (!ct_fits(ct, b->ct)) return narrowing(ct, b->ct);
+    if (n == 0) return EC_OK;
+    const size_t new_len = b->len + n, sz = kSize[b->ct];
+    void* grown;
+    EC_TRY(dev_alloc(&grown, new_len * sz));
+    if (b->len) EC_CUDA_TRY(cudaMemcpyAsync(grown, b->dptr, b->len * sz, cudaMemcpyDeviceToDevice, cur_stream()), "cudaMemcpyAsync(D2D)");
+    char* dst = static_cast<char*>(grown) + b->len * sz;
+    if (ct == b->ct) {
+        EC_CUDA_TRY(cudaMemcpyAsync(dst, host, n * sz, cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
+    } else {
+        void* stage;
+        EC_TRY(dev_alloc(&stage, n * kSize[ct]));
+        EC_CUDA_TRY(cudaMemcpyAsync(stage, host, n * kSize[ct], cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
+        // the appended run starts at an arbitrary cell offset: cast into an aligned temp, then copy
+        void* conv;
+        EC_TRY(dev_alloc(&conv, n * sz));
+        EC_LAUNCH(launch_convert(launch_ctx(), ct, stage, b->ct, conv, n), "convert");
+        EC_CUDA_TRY(cudaMemcpyAsync(dst, conv, n * sz, cudaMemcpyDeviceToDevice, cur_stream()), "cudaMemcpyAsync(D2D)");
+        dev_free(stage);
+        dev_free(conv);
+    }
+    EC_TRY(sync_stream());  // `host` may be reused by the caller as soon as we return
+    dev_free(b->dptr);
+    b->dptr = grown;
+    b->len = new_len;
+    b->capacity_bytes = new_len * sz;
+    return EC_OK;
+}
+
+// an empty result is UInt8([]) — FromIterator<CellValue>, src/buffer.rs:233-236
+static ec_status empty_result(ec_buf** out) { return new_buf(EC_UINT8, 0, out); }
+
+ec_status ec_buf_binary(int op, const ec_buf* l, const ec_buf* r, ec_buf** out) {
+    EC_TRY(ensure());
+    if (op < 0 || op > 3) return invalid("op");
+    const size_t n = std::min(l->len, r->len);  // zip (src/buffer.rs:327)
+    if (n == 0) return empty_result(out);
+    ec_buf* o;
+    EC_TRY(new_buf(EC_FLOAT64, n, &o));
+    if (cudaError_t e = launch_binary(launch_ctx(), op, l->ct, l->dptr, r->ct, r->dptr, static_cast<double*>(o->dptr), n, nullptr, nullptr, nullptr)) {
+        ec_buf_free(o);
+        return cuda_fail(e, "binary");
+    }
+    note_launch("binary");
+    *out = o;
+    return EC_OK;
+}
+ec_status ec_buf_scalar(int op, const ec_buf* l, const ec_value* r, ec_buf** out) {
+    EC_TRY(ensure());
+    if (op < 0 || op > 3 || !ct_ok(r->ct)) return invalid("op / cell type");
+    if (l->len == 0) return empty_result(out);
+    ec_buf* o;
+    EC_TRY(new_buf(EC_FLOAT64, l->len, &o));
+    // unify() is value-exact, so the rhs the reference feeds to the f64 op is `r as f64`
+    const double s = value_as_f64(*r);
+    if (cudaError_t e = launch_scalar(launch_ctx(), op, l->ct, l->dptr, s, static_cast<double*>(o->dptr), l->len)) {
+        ec_buf_free(o);
+        return cuda_fail(e, "scalar");
+    }
+    note_launch("scalar");
+    *out = o;
+    return EC_OK;
+}
+static const uint8_t kNegOut[10] = {EC_INT16, EC_INT32, EC_FLOAT64, EC_FLOAT64, EC_INT8, EC_INT16, EC_INT32, EC_INT64, EC_FLOAT32, EC_FLOAT64};
+ec_status ec_buf_neg(const ec_buf* b, ec_buf** out) {
+    EC_TRY(ensure());
+    if (b->len == 0) return empty_result(out);
+    ec_buf* o;
+    EC_TRY(new_buf(kNegOut[b->ct], b->len, &o));
+    if (cudaError_t e = launch_neg(launch_ctx(), b->ct, b->dptr, o->dptr, b->len)) { ec_buf_free(o); return cuda_fail(e, "neg"); }
+    note_launch("neg");
+    *out = o;
+    return EC_OK;
+}
+ec_status ec_buf_convert(const ec_buf* b, uint8_t ct, ec_buf** out) {
+    EC_TRY(ensure());
+    if (!ct_ok(ct)) return invalid("cell type");
+    if (ct == b->ct) return ec_buf_clone(b, out);            // src/buffer.rs:151-153
+    if (!ct_fits(b->ct, ct)) return narrowing(b->ct, ct);    // src/buffer.rs:155-159, before any launch
+    if (b->len == 0) return empty_result(out);               // collect() of nothing, src/buffer.rs:234
+    ec_buf* o;
+    EC_TRY(new_buf(ct, b->len, &o));
+    if (cudaError_t e = launch_convert(launch_ctx(), b->ct, b->dptr, ct, o->dptr, b->len)) { ec_buf_free(o); return cuda_fail(e, "convert"); }
+    note_launch("convert");
+    *out = o;
+    return EC_OK;
+}
+ec_status ec_buf_min_max(const ec_buf* b, const ec_mask* m, ec_value* mn, ec_value* mx) {
+    EC_TRY(ensure());
+    if (m && m->len != b->len) { set_error("Mask and buffer must have the same length."); return EC_LEN_MISMATCH; }
+    uint64_t k[2];
+    key_seeds(b->ct, &k[0], &k[1]);
+    if (b->len) {
+        ReduceScratch sc;
+        EC_TRY(run_min_max(b, m, &sc));
+        uint64_t* pin;
+        EC_TRY(pinned_words(&pin));
+        EC_CUDA_TRY(cudaMemcpyAsync(pin, sc.result, 16, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
+        EC_TRY(sync_stream());
+        k[0] = pin[0];
+        k[1] = pin[1];
+    }
+    *mn = tagged<uint64_t>(b->ct, key_to_bits(b->ct, k[0]));
+    *mx = tagged<uint64_t>(b->ct, key_to_bits(b->ct, k[1]));
+    return EC_OK;
+}
+ec_status ec_buf_cmp(const ec_buf* l, const ec_buf* r, int* ordering) {
+    EC_TRY(ensure());
+    if (l->ct != r->ct) { *ordering = l->ct < r->ct ? -1 : 1; return EC_OK; }  // src/buffer.rs:395-398
+    const size_t n = std::min(l->len, r->len);
+    if (n) {
+        ReduceScratch sc;
+        EC_TRY(reduce_scratch(&sc));
+        EC_LAUNCH(launch_first_diff(launch_ctx(), (int)kSize[l->ct], l->dptr, r->dptr, n, sc), "first_diff");
+        uint64_t* pin;
+        EC_TRY(pinned_words(&pin));
+        EC_CUDA_TRY(cudaMemcpyAsync(pin, sc.result, 16, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
+        EC_TRY(sync_stream());
+        const uint64_t idx = pin[0];
+        if (idx != ~0ull) {
+            ec_value a, b;
+            EC_TRY(ec_buf_get(l, idx, &a));
+            EC_TRY(ec_buf_get(r, idx, &b));
+            *ordering = value_cmp(a, b);
+            return EC_OK;
+        }
+    }
+    *ordering = l->len < r->len ? -1 : (l->len > r->len ? 1 : 0);
+    return EC_OK;
+}
+
+// ---- fused chains --------------------------------------------------------------------------------------
+ec_status ec_buf_normalized_difference(const ec_buf* a, const ec_buf* b, ec_buf** out) {
+    EC_TRY(ensure());
+    const size_t n = std::min(a->len, b->len);
+    if (n == 0) return empty_result(out);
+    ec_buf* o;
+    EC_TRY(new_buf(EC_FLOAT64, n, &o));
+    if (cudaError_t e = launch_normdiff(launch_ctx(), a->ct, a->dptr, b->ct, b->dptr, static_cast<double*>(o->dptr), n)) { ec_buf_free(o); return cuda_fail(e, "normdiff"); }
+    note_launch("normalized_difference");
+    *out = o;
+    return EC_OK;
+}
+ec_status ec_buf_binary_scalar(int op1, const ec_buf* l, const ec_buf* r, int op2, const ec_value* s, ec_buf** out) {
+    EC_TRY(ensure());
+    if (op1 < 0 || op1 > 3 || op2 < 0 || op2 > 3 || !ct_ok(s->ct)) return invalid("op / cell type");
+    const size_t n = std::min(l->len, r->len);
+    if (n == 0) return empty_result(out);
+    ec_buf* o;
+    EC_TRY(new_buf(EC_FLOAT64, n, &o));
+    if (cudaError_t e = launch_binary_scalar(launch_ctx(), op1, l->ct, l->dptr, r->ct, r->dptr, op2, value_as_f64(*s), static_cast<double*>(o->dptr), n)) { ec_buf_free(o); return cuda_fail(e, "binary_scalar"); }
+    note_launch("binary_scalar");
+    *out = o;
+    return EC_OK;
+}
+
+// ---- Mask ------------------------------------------------------------------------------------------------
+ec_status ec_mask_from_bools(const uint8_t* host_bools, size_t len, ec_mask** out) {
+    EC_TRY(ensure());
+    ec_mask* m;
+    EC_TRY(new_mask(len, &m));
+    if (len) {
+        void* stage;
+        EC_TRY(dev_alloc(&stage, len));
+        EC_CUDA_TRY(cudaMemcpyAsync(stage, host_bools, len, cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
+        EC_LAUNCH(launch_mask_build(launch_ctx(), 1, stage, len, 0, true, m->words), "mask_pack");
+        dev_free(stage);
+    }
+    *out = m;
+    return EC_OK;
+}
+ec_status ec_mask_fill(size_t len, int value, ec_mask** out) {
+    EC_TRY(ensure());
+    ec_mask* m;
+    EC_TRY(new_mask(len, &m));
+    if (len) EC_LAUNCH(launch_mask_fill(launch_ctx(), m->words, len, value != 0), "mask_fill");
+    *out = m;
+    return EC_OK;
+}
+ec_status ec_mask_to_bools(const ec_mask* m, uint8_t* host_bools, size_t capacity) {
+    EC_TRY(ensure());
+    if (capacity < m->len) return invalid("ec_mask_to_bools: host buffer too small");
+    if (m->len == 0) return EC_OK;
+    void* stage;
+    EC_TRY(dev_alloc(&stage, m->len));
+    EC_LAUNCH(launch_mask_unpack(launch_ctx(), m->words, m->len, static_cast<uint8_t*>(stage)), "mask_unpack");
+    EC_CUDA_TRY(cudaMemcpyAsync(host_bools, stage, m->len, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
+    dev_free(stage);
+    return sync_stream();
+}
+ec_status ec_mask_clone(const ec_mask* m, ec_mask** out) {
+    EC_TRY(ensure());
+    ec_mask* c;
+    EC_TRY(new_mask(m->len, &c));
+    if (m->len) EC_CUDA_TRY(cudaMemcpyAsync(c->words, m->words, ((m->len + 31) / 32) * 4, cudaMemcpyDeviceToDevice, cur_stream()), "cudaMemcpyAsync(D2D)");
+    *out = c;
+    return EC_OK;
+}
+void ec_mask_free(ec_mask* m) {
+    if (!m) return;
+    dev_free(m->words);
+    delete m;
+}
+size_t ec_mask_len(const ec_mask* m) { return m->len; }
+void* ec_mask_device_words(const ec_mask* m) { return m->words; }
+static ec_status mask_word(const ec_mask* m, size_t w, uint32_t* out) {
+    uint64_t* pin;
+    EC_TRY(pinned_words(&pin));
+    EC_CUDA_TRY(cudaMemcpyAsync(pin, m->words + w, 4, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
+    EC_TRY(sync_stream());
+    *out = static_cast<uint32_t>(pin[0]);
+    return EC_OK;
+}
+ec_status ec_mask_get(const ec_mask* m, size_t index, int* out) {
+    EC_TRY(ensure());
+    if (index >= m->len) { set_error("index out of bounds: the len is %zu but the index is %zu", m->len, index); return EC_OOB; }
+    uint32_t w;
+    EC_TRY(mask_word(m, index / 32, &w));
+    *out = (w >> (index % 32)) & 1u;
+    return EC_OK;
+}
+ec_status ec_mask_put(ec_mask* m, size_t index, int value) {
+    EC_TRY(ensure());
+    if (index >= m->len) { set_error("index out of bounds: the len is %zu but the index is %zu", m->len, index); return EC_OOB; }
+    uint32_t w;
+    EC_TRY(mask_word(m, index / 32, &w));
+    const uint32_t bit = 1u << (index % 32);
+    w = value ? (w | bit) : (w & ~bit);
+    uint64_t* pin;
+    EC_TRY(pinned_words(&pin));
+    pin[1] = w;
+    EC_CUDA_TRY(cudaMemcpyAsync(m->words + index / 32, &pin[1], 4, cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
+    return sync_stream();
+}
+ec_status ec_mask_extend_host(ec_mask* m, const uint8_t* host_bools, size_t n) {
+    EC_TRY(ensure());
+    if (n == 0) return EC_OK;
+    // unpack -> append -> repack on the device (Extend is not a bulk path in the reference either)
+    const size_t new_len = m->len + n;
+    void* stage;
+    EC_TRY(dev_alloc(&stage, new_len));
+    if (m->len) EC_LAUNCH(launch_mask_unpack(launch_ctx(), m->words, m->len, static_cast<uint8_t*>(stage)), "mask_unpack");
+    EC_CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(stage) + m->len, host_bools, n, cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
+    void* words;
+    EC_TRY(dev_alloc(&words, mask_bytes(new_len)));
+    EC_LAUNCH(launch_mask_build(launch_ctx(), 1, stage, new_len, 0, true, static_cast<uint32_t*>(words)), "mask_pack");
+    dev_free(stage);
+    EC_TRY(sync_stream());
+    dev_free(m->words);
+    m->words = static_cast<uint32_t*>(words);
+    m->len = new_len;
+    m->capacity_bytes = mask_bytes(new_len);
+    return EC_OK;
+}
+static ec_status mask_bitop(int mop, const ec_mask* l, const ec_mask* r, ec_mask** out) {
+    EC_TRY(ensure());
+    const size_t n = r ? std::min(l->len, r->len) : l->len;  // zip (src/masked/mask.rs:133-137)
+    ec_mask* o;
+    EC_TRY(new_mask(n, &o));
+    if (n) EC_LAUNCH(launch_mask_bitop(launch_ctx(), mop, l->words, r ? r->words : nullptr, n, o->words), "mask_bitop");
+    *out = o;
+    return EC_OK;
+}
+ec_status ec_mask_not(const ec_mask* m, ec_mask** out) { return mask_bitop(0, m, nullptr, out); }
+ec_status ec_mask_and(const ec_mask* l, const ec_mask* r, ec_mask** out) { return mask_bitop(1, l, r, out); }
+ec_status ec_mask_or(const ec_mask* l, const ec_mask* r, ec_mask** out) { return mask_bitop(2, l, r, out); }
+static ec_status mask_popcount_device(const ec_mask* m, ReduceScratch* sc) {
+    EC_TRY(reduce_scratch(sc));
+    EC_LAUNCH(launch_popcount(launch_ctx(), m->words, (m->len + 31) / 32, *sc), "mask_counts");
+    return EC_OK;
+}
+ec_status ec_mask_counts(const ec_mask* m, size_t* data, size_t* nodata) {
+    EC_TRY(ensure());
+    uint64_t ones = 0;
+    if (m->len) {
+        ReduceScratch sc;
+        EC_TRY(mask_popcount_device(m, &sc));
+        uint64_t* pin;
+        EC_TRY(pinned_words(&pin));
+        EC_CUDA_TRY(cudaMemcpyAsync(pin, sc.result, 16, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
+        EC_TRY(sync_stream());
+        ones = pin[0];
+    }
+    *data = ones;
+    *nodata = m->len - ones;
+    return EC_OK;
+}
+ec_status ec_mask_all(const ec_mask* m, int value, int* out) {
+    size_t d, nd;
+    EC_TRY(ec_mask_counts(m, &d, &nd));
+    *out = value ? (nd == 0) : (d == 0);
+    return EC_OK;
+}
+ec_status ec_mask_cmp(const ec_mask* l, const ec_mask* r, int* ordering) {
+    EC_TRY(ensure());
+    const size_t n = std::min(l->len, r->len);
+    if (n) {
+        ReduceScratch sc;
+        EC_TRY(reduce_scratch(&sc));
+        EC_LAUNCH(launch_first_diff(launch_ctx(), 4, l->words, r->words, (n + 31) / 32, sc), "first_diff");
+        uint64_t* pin;
+        EC_TRY(pinned_words(&pin));
+        EC_CUDA_TRY(cudaMemcpyAsync(pin, sc.result, 16, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
+        EC_TRY(sync_stream());
+        const uint64_t w = pin[0];
+        if (w != ~0ull) {
+            uint32_t a, b;
+            EC_TRY(mask_word(l, w, &a));
+            EC_TRY(mask_word(r, w, &b));
+            const size_t bit = w * 32 + __builtin_ctz(a ^ b);
+            if (bit < n) { *ordering = ((a >> (bit % 32)) & 1u) ? 1 : -1; return EC_OK; }  // false < true
+        }
+    }
+    *ordering = l->len < r->len ? -1 : (l->len > r->len ? 1 : 0);
+    return EC_OK;
+}
+
+// ---- MaskedCellBuffer / NoData ------------------------------------------------------------------------------
+ec_status ec_nodata_value(int kind, uint8_t ct, const ec_value* v, ec_value* out, int* has_value) {
+    if (!ct_ok(ct) || kind < 0 || kind > 2 || (kind == EC_NODATA_VALUE && !v)) return invalid("nodata");
+    *has_value = nodata_sentinel(kind, ct, v, out);
+    return EC_OK;
+}
+ec_status ec_mask_from_nodata(const ec_buf* b, int kind, const ec_value* v, ec_mask** out) {
+    EC_TRY(ensure());
+    if (kind < 0 || kind > 2 || (kind == EC_NODATA_VALUE && !v)) return invalid("nodata");
+    ec_value nd;
+    if (!nodata_sentinel(kind, b->ct, v, &nd)) return ec_mask_fill(b->len, 1, out);  // NoData::None: all valid
+    if (nd.ct != b->ct) return invalid("NoData<T>: T must be the buffer's cell type");
+    ec_mask* m;
+    EC_TRY(new_mask(b->len, &m));
+    if (b->len) EC_LAUNCH(launch_mask_build(launch_ctx(), (int)kSize[b->ct], b->dptr, b->len, nd.bits, false, m->words), "mask_from_nodata");
+    *out = m;
+    return EC_OK;
+}
+ec_status ec_buf_fill_nodata(const ec_buf* b, const ec_mask* m, uint8_t dst_ct, int kind, const ec_value* v, ec_buf** out) {
+    EC_TRY(ensure());
+    if (!ct_ok(dst_ct) || kind < 0 || kind > 2 || (kind == EC_NODATA_VALUE && !v)) return invalid("nodata / cell type");
+    if (!ct_fits(b->ct, dst_ct)) return narrowing(b->ct, dst_ct);  // to_vec::<T>()? first (src/masked/masked_buffer.rs:142)
+    ec_value nd;
+    if (!nodata_sentinel(kind, dst_ct, v, &nd)) return ec_buf_convert(b, dst_ct, out);
+    if (nd.ct != dst_ct) return invalid("NoData<T>: T must be the target cell type");
+    if (m->len != b->len) { set_error("Mask and buffer must have the same length."); return EC_LEN_MISMATCH; }
+    ec_buf* o;
+    EC_TRY(new_buf(dst_ct, b->len, &o));
+    if (b->len) {
+        if (cudaError_t e = launch_fill_nodata(launch_ctx(), b->ct, b->dptr, m->words, dst_ct, o->dptr, b->len, nd.bits)) { ec_buf_free(o); return cuda_fail(e, "fill_nodata"); }
+        note_launch("fill_nodata");
+    }
+    *out = o;
+    return EC_OK;
+}
+ec_status ec_masked_binary(int op, const ec_buf* lbuf, const ec_mask* lmask, const ec_buf* rbuf, const ec_mask* rmask,
+                           ec_buf** out_buf, ec_mask** out_mask) {
+    EC_TRY(ensure());
+    if (op < 0 || op > 3) return invalid("op");
+    if (lmask->len != lbuf->len || rmask->len != rbuf->len) { set_error("Mask and buffer must have the same length."); return EC_LEN_MISMATCH; }
+    const size_t n = std::min(lbuf->len, rbuf->len);
+    ec_mask* om;
+    EC_TRY(new_mask(n, &om));
+    if (n == 0) { *out_mask = om; return empty_result(out_buf); }
+    ec_buf* o;
+    if (ec_status s = new_buf(EC_FLOAT64, n, &o)) { ec_mask_free(om); return s; }
+    // The shorter operand's mask has no bits past n, so `&` leaves the last word's tail zero.
+    if (cudaError_t e = launch_binary(launch_ctx(), op, lbuf->ct, lbuf->dptr, rbuf->ct, rbuf->dptr, static_cast<double*>(o->dptr), n,
+                                      lmask->words, rmask->words, om->words)) {
+        ec_buf_free(o); ec_mask_free(om);
+        return cuda_fail(e, "masked_binary");
+    }
+    note_launch("masked_binary");
+    *out_buf = o;
+    *out_mask = om;
+    return EC_OK;
+}
+
+// ---- sharding ---------------------------------------------------------------------------------------------------
+ec_status ec_row_strip(size_t width, size_t height, int n_shards, int shard, size_t* cell_offset, size_t* cell_len) {
+    if (n_shards <= 0 || shard < 0 || shard >= n_shards) return invalid("shard index");
+    const size_t total = width * height, g = (size_t)shard, G = (size_t)n_shards;
+    if (G == 1) { *cell_offset = 0; *cell_len = total; return EC_OK; }
+    if (width % 128 == 0) {  // whole rows, remainder rows to the last strip
+        const size_t rows = height / G, r0 = g * rows, r1 = (g + 1 == G) ? height : r0 + rows;
+        *cell_offset = r0 * width;
+        *cell_len = (r1 - r0) * width;
+    } else {  // 128-cell aligned cell ranges
+        const size_t per = (total / G) & ~size_t(127), c0 = g * per, c1 = (g + 1 == G) ? total : c0 + per;
+        *cell_offset = c0;
+        *cell_len = c1 - c0;
+    }
+    return EC_OK;
+}
+ec_status ec_buf_min_max_keys(const ec_buf* b, const ec_mask* m, int64_t* device_keys2) {
+    EC_TRY(ensure());
+    if (m && m->len != b->len) { set_error("Mask and buffer must have the same length."); return EC_LEN_MISMATCH; }
+    if (b->len == 0) {  // the seeds alone (src/buffer.rs:170)
+        uint64_t seed[2];
+        key_seeds(b->ct, &seed[0], &seed[1]);
+        uint64_t* pin;
+        EC_TRY(pinned_words(&pin));
+        pin[2] = (uint64_t)key_to_signed(seed[0]);
+        pin[3] = (uint64_t)~key_to_signed(seed[1]);
+        EC_CUDA_TRY(cudaMemcpyAsync(device_keys2, &pin[2], 16, cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
+        return sync_stream();
+    }
+    ReduceScratch sc;
+    EC_TRY(run_min_max(b, m, &sc));
+    // the finishing CTA also wrote {skey(min), ~skey(max)}: one MIN all-reduce finishes both. No host round trip.
+    EC_CUDA_TRY(cudaMemcpyAsync(device_keys2, sc.result + 2, 16, cudaMemcpyDeviceToDevice, cur_stream()), "cudaMemcpyAsync(D2D)");
+    return EC_OK;
+}
+ec_status ec_min_max_from_keys(uint8_t ct, const int64_t* k, ec_value* mn, ec_value* mx) {
+    if (!ct_ok(ct)) return invalid("cell type");
+    *mn = tagged<uint64_t>(ct, key_to_bits(ct, key_from_signed(k[0])));
+    *mx = tagged<uint64_t>(ct, key_to_bits(ct, key_from_signed(~k[1])));
+    return EC_OK;
+}
+
+ec_status ec_buf_synth(uint8_t ct, size_t len, uint64_t seed, uint64_t index_offset, int kind, double lo, double hi,
+                       uint64_t period, const ec_value* sentinel, ec_buf** out) {
+    EC_TRY(ensure());
+    if (!ct_ok(ct) || kind < 0 || kind > 2) return invalid("cell type / kind");
+    ec_buf* b;
+    EC_TRY(new_buf(ct, len, &b));
+    if (len) {
+        if (cudaError_t e = launch_synth(launch_ctx(), ct, b->dptr, len, seed, index_offset, kind, lo, hi,
+                                         sentinel ? period : 0, sentinel ? sentinel->bits : 0)) { ec_buf_free(b); return cuda_fail(e, "synth"); }
+        note_launch("synth");
+    }
+    *out = b;
+    return EC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,218 @@
+// Reductions: min_max (src/buffer.rs:169-173, masked: src/masked/masked_buffer.rs:208-217),
+// Mask::counts / Mask::all (src/masked/mask.rs:67-80) and the first-difference search behind
+// Ord/Eq for CellBuffer (src/buffer.rs:390-436). Read-only streams: algorithmic bytes per cell =
+// size_of(T) (+ 1/8 with a mask).
+//
+// Shape: 256-bit loads, UNROLL independent requests per thread -> per-thread accumulators on
+// order-preserving unsigned keys -> warp redux/shuffle -> shared-memory block tree -> one partial
+// per CTA -> the last CTA to finish (atomic ticket) folds the partials and writes the result. One
+// launch, no float atomics, exactly associative, so the answer does not depend on the grid.
+#pragma once
+#include "ec_common.cuh"
+
+namespace ec {
+
+struct ReduceScratch {
+    uint64_t* partials;     // 2 * max_blocks
+    unsigned int* ticket;   // zero between launches (the finishing CTA resets it)
+    uint64_t* result;       // 4 words: [0..1] raw result; [2..3] min_max as {skey(min), ~skey(max)} for a MIN all-reduce
+};
+
+__device__ __forceinline__ uint32_t warp_min(uint32_t v) { return __reduce_min_sync(0xFFFFFFFFu, v); }
+__device__ __forceinline__ uint32_t warp_max(uint32_t v) { return __reduce_max_sync(0xFFFFFFFFu, v); }
+__device__ __forceinline__ uint64_t warp_min(uint64_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { uint64_t x = __shfl_xor_sync(0xFFFFFFFFu, v, o); v = x < v ? x : v; }
+    return v;
+}
+__device__ __forceinline__ uint64_t warp_max(uint64_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { uint64_t x = __shfl_xor_sync(0xFFFFFFFFu, v, o); v = x > v ? x : v; }
+    return v;
+}
+__device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+enum : int { RED_MINMAX = 0, RED_SUM = 1, RED_MIN = 2 };
+
+template <int MODE> __device__ __forceinline__ void combine(uint64_t& a0, uint64_t& a1, uint64_t b0, uint64_t b1) {
+    if constexpr (MODE == RED_MINMAX) { a0 = b0 < a0 ? b0 : a0; a1 = b1 > a1 ? b1 : a1; }
+    else if constexpr (MODE == RED_SUM) { a0 += b0; a1 += b1; }
+    else { a0 = b0 < a0 ? b0 : a0; a1 = b1 < a1 ? b1 : a1; }
+}
+
+// Block tree + cross-CTA finish. (k0,k1) are this thread's warp-reduced values (valid in lane 0).
+template <int MODE, int THREADS>
+__device__ __forceinline__ void block_finish(uint64_t k0, uint64_t k1, uint64_t id0, uint64_t id1, ReduceScratch s) {
+    __shared__ uint64_t sh0[THREADS / 32], sh1[THREADS / 32];
+    __shared__ bool last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sh0[warp] = k0; sh1[warp] = k1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t a0 = sh0[0], a1 = sh1[0];
+#pragma unroll
+        for (int w = 1; w < THREADS / 32; ++w) combine<MODE>(a0, a1, sh0[w], sh1[w]);
+        s.partials[2 * blockIdx.x] = a0;
+        s.partials[2 * blockIdx.x + 1] = a1;
+        __threadfence();
+        const unsigned int done = atomicAdd(s.ticket, 1u);
+        last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    uint64_t a0 = id0, a1 = id1;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += THREADS) {
+        combine<MODE>(a0, a1, __ldcg(s.partials + 2 * i), __ldcg(s.partials + 2 * i + 1));
+    }
+    if constexpr (MODE == RED_MINMAX) { a0 = warp_min(a0); a1 = warp_max(a1); }
+    else if constexpr (MODE == RED_SUM) { a0 = warp_sum(a0); a1 = warp_sum(a1); }
+    else { a0 = warp_min(a0); a1 = warp_min(a1); }
+    __syncthreads();
+    if (lane == 0) { sh0[warp] = a0; sh1[warp] = a1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a0 = sh0[0]; a1 = sh1[0];
+#pragma unroll
+        for (int w = 1; w < THREADS / 32; ++w) combine<MODE>(a0, a1, sh0[w], sh1[w]);
+        s.result[0] = a0;
+        s.result[1] = a1;
+        if constexpr (MODE == RED_MINMAX) {  // order-preserving signed keys, max negated
+            s.result[2] = a0 ^ 0x8000000000000000ull;
+            s.result[3] = ~(a1 ^ 0x8000000000000000ull);
+        }
+        *s.ticket = 0;  // ready for the next launch on this stream
+    }
+}
+
+// ---- min_max ---------------------------------------------------------------------------------
+// Unmasked 8/16-bit cells are reduced two-at-a-time in packed 16-bit lanes (VIMNMX.U16x2); wider
+// cells and the masked flavour go cell by cell on 32/64-bit keys.
+template <class T, bool MASKED, int VB, int UNROLL, int THREADS>
+__global__ void __launch_bounds__(THREADS) min_max_kernel(const T* __restrict__ a, const uint32_t* __restrict__ m,
+                                                          size_t n, okey_t<T> seed_min, okey_t<T> seed_max,
+                                                          ReduceScratch s) {
+    using K = okey_t<T>;
+    constexpr int V = VB / sizeof(T);
+    constexpr size_t TILE = size_t(THREADS) * V * UNROLL;
+    const size_t full = n / TILE;
+    K kmin = seed_min, kmax = seed_max;
+
+    if constexpr (!MASKED && sizeof(T) <= 2) {
+        constexpr bool SG = std::is_signed<T>::value;
+        constexpr uint32_t BIAS = sizeof(T) == 1 ? (SG ? 0x80808080u : 0u) : (SG ? 0x80008000u : 0u);
+        uint32_t pmin = 0xFFFFFFFFu, pmax = 0u;  // two 16-bit lanes of biased keys
+        for (size_t t = blockIdx.x; t < full; t += gridDim.x) {
+            const size_t base = t * TILE + size_t(threadIdx.x) * V;
+            Vec<uint32_t, VB / 4> w[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+                w[u] = ld_stream<uint32_t, VB / 4>(reinterpret_cast<const uint32_t*>(a + base + size_t(u) * THREADS * V));
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+                for (int j = 0; j < VB / 4; ++j) {
+                    const uint32_t x = w[u].v[j] ^ BIAS;
+                    if constexpr (sizeof(T) == 2) {
+                        pmin = __vminu2(pmin, x);
+                        pmax = __vmaxu2(pmax, x);
+                    } else {
+                        const uint32_t e = __byte_perm(x, 0u, 0x4240), o = __byte_perm(x, 0u, 0x4341);
+                        pmin = __vimin3_u16x2(pmin, e, o);
+                        pmax = __vimax3_u16x2(pmax, e, o);
+                    }
+                }
+            }
+        }
+        // unbias back into the generic 32-bit key domain
+        constexpr uint32_t LB = sizeof(T) == 1 ? (SG ? 0x80u : 0u) : (SG ? 0x8000u : 0u);
+        const uint32_t lo = min(pmin & 0xFFFFu, pmin >> 16), hi = max(pmax & 0xFFFFu, pmax >> 16);
+        if (full > 0 && blockIdx.x < full) {
+            // biased narrow key -> value -> 32-bit key
+            const T vlo = static_cast<T>(static_cast<bits_t<T>>(lo ^ LB)), vhi = static_cast<T>(static_cast<bits_t<T>>(hi ^ LB));
+            const K klo = to_key<T>(vlo), khi = to_key<T>(vhi);
+            kmin = klo < kmin ? klo : kmin;
+            kmax = khi > kmax ? khi : kmax;
+        }
+    } else {
+        constexpr uint32_t VMASK = V >= 32 ? 0xFFFFFFFFu : ((1u << (V & 31)) - 1u);
+        for (size_t t = blockIdx.x; t < full; t += gridDim.x) {
+            const size_t base = t * TILE + size_t(threadIdx.x) * V;
+            Vec<T, V> va[UNROLL];
+            uint32_t w[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const size_t c = base + size_t(u) * THREADS * V;
+                va[u] = ld_stream<T, V>(a + c);
+                if constexpr (MASKED) w[u] = (__ldg(m + c / 32) >> (c % 32)) & VMASK;
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const K k = to_key<T>(va[u].v[j]);
+                    if constexpr (MASKED) {
+                        const bool valid = (w[u] >> j) & 1u;
+                        kmin = (valid && k < kmin) ? k : kmin;
+                        kmax = (valid && k > kmax) ? k : kmax;
+                    } else {
+                        kmin = k < kmin ? k : kmin;
+                        kmax = k > kmax ? k : kmax;
+                    }
+                }
+            }
+        }
+    }
+    if (blockIdx.x == full % gridDim.x) {
+        for (size_t i = full * TILE + threadIdx.x; i < n; i += THREADS) {
+            bool valid = true;
+            if constexpr (MASKED) valid = (m[i / 32] >> (i % 32)) & 1u;
+            const K k = to_key<T>(a[i]);
+            kmin = (valid && k < kmin) ? k : kmin;
+            kmax = (valid && k > kmax) ? k : kmax;
+        }
+    }
+    kmin = warp_min(kmin);
+    kmax = warp_max(kmax);
+    block_finish<RED_MINMAX, THREADS>(kmin, kmax, seed_min, seed_max, s);
+}
+
+// ---- Mask::counts: popcount over packed words (tail bits beyond len are kept zero) ---------------
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) popcount_kernel(const uint32_t* __restrict__ m, size_t words, ReduceScratch s) {
+    uint64_t c = 0;
+    const size_t groups = words / 4;  // 16-byte groups (allocation is padded to 16 bytes, pad is zero)
+    for (size_t g = blockIdx.x * size_t(THREADS) + threadIdx.x; g < groups; g += size_t(gridDim.x) * THREADS) {
+        const Vec<uint32_t, 4> w = ld_stream<uint32_t, 4>(m + 4 * g);
+        c += __popc(w.v[0]) + __popc(w.v[1]) + __popc(w.v[2]) + __popc(w.v[3]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < words % 4) c += __popc(m[groups * 4 + threadIdx.x]);
+    c = warp_sum(c);
+    block_finish<RED_SUM, THREADS>(c, 0, 0, 0, s);
+}
+
+// ---- first differing cell of two buffers of the same type (bitwise == total-order equality) -------
+template <class T, int VB, int THREADS>
+__global__ void __launch_bounds__(THREADS) first_diff_kernel(const T* __restrict__ a, const T* __restrict__ b, size_t n,
+                                                             ReduceScratch s) {
+    constexpr int V = VB / sizeof(T);
+    uint64_t first = ~0ull;
+    const size_t groups = n / V;
+    for (size_t g = blockIdx.x * size_t(THREADS) + threadIdx.x; g < groups; g += size_t(gridDim.x) * THREADS) {
+        const Vec<T, V> x = ld_stream<T, V>(a + g * V), y = ld_stream<T, V>(b + g * V);
+#pragma unroll
+        for (int j = V - 1; j >= 0; --j)
+            if (to_bits(x.v[j]) != to_bits(y.v[j])) { const uint64_t i = g * V + j; first = i < first ? i : first; }
+    }
+    if (blockIdx.x == 0)
+        for (size_t i = groups * V + threadIdx.x; i < n; i += THREADS)
+            if (to_bits(a[i]) != to_bits(b[i])) first = i < first ? i : first;
+    first = warp_min(first);
+    block_finish<RED_MIN, THREADS>(first, ~0ull, ~0ull, ~0ull, s);
+}
+
+}  // namespace ec

@@ -1,0 +1,244 @@
+/*
+ * erased_cells_b200 — C ABI of the B200-native per-cell compute path of s22s/erased-cells.
+ *
+ * This header is the drop-in boundary. The reference crate (v0.1.1) has no FFI of its own: its
+ * boundary is the public Rust API — trait `BufferOps` (src/lib.rs:104-163), the `std::ops` impls on
+ * `CellBuffer` (src/buffer.rs:321-371) and `MaskedCellBuffer` (src/masked/masked_buffer.rs:323-383),
+ * `Mask` (src/masked/mask.rs:14-164), `NoData` (src/masked/nodata.rs:9-68), `CellType`
+ * (src/ctype.rs) and `CellValue` (src/value.rs). Each entry point below names the reference item
+ * whose body it replaces; INTEGRATION.md shows the Rust `extern "C"` block and the `impl` bodies a
+ * maintainer would write over it, include/erased_cells.hpp is the same mirror in C++ and
+ * erased_cells_b200/ (Python, ctypes) is the one the parity tests drive.
+ *
+ * Conventions
+ *   - Plain C types only. Buffers and masks are opaque handles to device-resident storage, owned
+ *     by exactly one caller-side value; every op returns a fresh handle and never mutates or
+ *     aliases its inputs (Rust ownership: `Drop` -> ec_*_free, `Clone` -> ec_*_clone).
+ *   - Every function returns ec_status (0 = ok) unless noted; ec_last_error() gives the
+ *     thread-local message of the last failure. No exceptions cross this boundary.
+ *   - One process drives one GPU (ec_init(device)); work is enqueued on the library's current
+ *     stream for the calling thread (ec_set_stream to share the caller's stream). Calls that
+ *     return host-visible results (min_max, counts, get, to_host, cmp) synchronise that stream.
+ *   - There is no CPU compute path: without a usable CUDA device every device entry point fails
+ *     with EC_NO_DEVICE.
+ *   - Cell types are the `CellType` discriminants (src/lib.rs:85-101): 0..9 =
+ *     UInt8, UInt16, UInt32, UInt64, Int8, Int16, Int32, Int64, Float32, Float64.
+ *   - Arithmetic semantics (src/value.rs:196-209): out[i] = (f64)l[i] OP (f64)r[i], IEEE-754
+ *     binary64, round to nearest even, no FMA contraction; the result buffer is always Float64
+ *     (UInt8 when empty, src/buffer.rs:234). NaN results carry the x86-64 SSE2 sign/payload the
+ *     reference produces on its platform (lhs NaN wins, else rhs NaN, quieted; invalid operation
+ *     -> 0xFFF8000000000000).
+ */
+#ifndef ERASED_CELLS_B200_H
+#define ERASED_CELLS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EC_ABI_VERSION 1
+
+/* Error conventions — src/error.rs:12-27. Only NarrowingError is reachable from the hot path
+ * (src/buffer.rs:155-159, src/value.rs:77-81); index panics (src/lib.rs:136-147) and the
+ * MaskedCellBuffer::new length assertion (src/masked/masked_buffer.rs:49-53) surface as EC_OOB /
+ * EC_LEN_MISMATCH so the host shim can panic/raise. */
+typedef enum ec_status {
+    EC_OK = 0,
+    EC_NARROWING = 1,     /* Error::NarrowingError{src,dst}; see ec_last_narrowing() */
+    EC_OOB = 2,           /* index >= len */
+    EC_LEN_MISMATCH = 3,  /* buffer/mask length mismatch */
+    EC_INVALID_ARG = 4,   /* bad cell type / op / null handle */
+    EC_CUDA = 5,          /* CUDA runtime error, message in ec_last_error() */
+    EC_NCCL = 6,          /* NCCL error or NCCL not loadable */
+    EC_OOM = 7,           /* device or pinned-host allocation failed */
+    EC_NO_DEVICE = 8,     /* no usable CUDA device: there is no CPU fallback */
+    EC_PARSE = 9          /* Error::ParseError (CellType::from_str) */
+} ec_status;
+
+typedef enum ec_ctype {
+    EC_UINT8 = 0, EC_UINT16 = 1, EC_UINT32 = 2, EC_UINT64 = 3,
+    EC_INT8 = 4, EC_INT16 = 5, EC_INT32 = 6, EC_INT64 = 7,
+    EC_FLOAT32 = 8, EC_FLOAT64 = 9
+} ec_ctype;
+
+typedef enum ec_op { EC_ADD = 0, EC_SUB = 1, EC_MUL = 2, EC_DIV = 3 } ec_op;
+
+/* NoData<T> — src/masked/nodata.rs:9-17 */
+typedef enum ec_nodata_kind { EC_NODATA_NONE = 0, EC_NODATA_DEFAULT = 1, EC_NODATA_VALUE = 2 } ec_nodata_kind;
+
+/* CellValue — src/value.rs:12-20: a 16-byte tagged scalar. `bits` holds the little-endian payload
+ * of the tagged primitive in its low size_of(ct) bytes, upper bytes zero. */
+typedef struct ec_value {
+    uint8_t ct;
+    uint8_t pad[7];
+    uint64_t bits;
+} ec_value;
+
+typedef struct ec_buf ec_buf;   /* CellBuffer: typed cells in HBM */
+typedef struct ec_mask ec_mask; /* Mask: validity bits in HBM, packed 32 cells per little-endian word */
+typedef struct ec_event ec_event;
+typedef struct ec_comm ec_comm;
+
+typedef struct ec_device_info {
+    int device;
+    int sm_count;
+    int cc_major, cc_minor;
+    size_t l2_bytes;
+    size_t total_mem_bytes;
+    char name[128];
+} ec_device_info;
+
+/* ---- library / device context -------------------------------------------------------------- */
+int ec_abi_version(void);
+const char* ec_last_error(void);
+/* src/error.rs:14: the {src, dst} of the last EC_NARROWING on this thread */
+void ec_last_narrowing(uint8_t* src, uint8_t* dst);
+ec_status ec_init(int device);           /* bind this process to one GPU; idempotent */
+ec_status ec_device_info_get(ec_device_info* out);
+ec_status ec_set_stream(void* cuda_stream); /* NULL restores the library's own stream */
+void* ec_get_stream(void);
+ec_status ec_synchronize(void);
+uint64_t ec_kernel_launches(void);       /* number of this library's kernels launched so far */
+/* name of the last kernel family launched by this thread (for profiles/bench bookkeeping) */
+const char* ec_last_kernel(void);
+ec_status ec_event_create(ec_event** out);
+ec_status ec_event_record(ec_event* e);  /* on the current stream */
+ec_status ec_event_elapsed_ms(ec_event* start, ec_event* stop, float* ms); /* synchronises `stop` */
+void ec_event_destroy(ec_event* e);
+/* pinned host staging for from_vec / to_vec (src/buffer.rs:64-66, :175-185) */
+ec_status ec_host_alloc(size_t bytes, void** out);
+void ec_host_free(void* p);
+ec_status ec_host_register(void* p, size_t bytes);
+ec_status ec_host_unregister(void* p);
+
+/* ---- CellType: host-side lattice — src/ctype.rs -------------------------------------------- */
+uint8_t ec_ctype_union(uint8_t a, uint8_t b);        /* src/ctype.rs:99-126 */
+int ec_ctype_can_fit_into(uint8_t a, uint8_t b);     /* src/ctype.rs:129-131 */
+size_t ec_ctype_size_of(uint8_t ct);                 /* src/ctype.rs:87-96 */
+int ec_ctype_is_integral(uint8_t ct);                /* src/ctype.rs:55-68 */
+int ec_ctype_is_signed(uint8_t ct);                  /* src/ctype.rs:71-84 */
+const char* ec_ctype_name(uint8_t ct);               /* Display, src/ctype.rs:23-27 */
+ec_status ec_ctype_from_name(const char* s, uint8_t* out); /* FromStr, src/ctype.rs:29-43 */
+ec_status ec_ctype_min_value(uint8_t ct, ec_value* out);   /* src/ctype.rs:158-167 */
+ec_status ec_ctype_max_value(uint8_t ct, ec_value* out);   /* src/ctype.rs:170-179 */
+ec_status ec_ctype_zero(uint8_t ct, ec_value* out);        /* src/ctype.rs:134-143 */
+ec_status ec_ctype_one(uint8_t ct, ec_value* out);         /* src/ctype.rs:146-155 */
+
+/* ---- CellValue: host-side scalar — src/value.rs -------------------------------------------- */
+ec_status ec_value_convert(const ec_value* v, uint8_t ct, ec_value* out);             /* :74-98 */
+ec_status ec_value_binary(int op, const ec_value* l, const ec_value* r, ec_value* out); /* :199-222 */
+ec_status ec_value_neg(const ec_value* v, ec_value* out);                             /* :224-240 */
+ec_status ec_value_cmp(const ec_value* l, const ec_value* r, int* ordering);          /* :248-265 */
+ec_status ec_value_to_f64(const ec_value* v, double* out, int* is_some);              /* :144-156 */
+ec_status ec_value_to_i64(const ec_value* v, int64_t* out, int* is_some);             /* :118-129 */
+ec_status ec_value_to_u64(const ec_value* v, uint64_t* out, int* is_some);            /* :131-142 */
+
+/* ---- CellBuffer — src/buffer.rs ------------------------------------------------------------- */
+/* from_vec / From<Vec<T>> / From<&[T]> (:64-66, :252-276): one H2D copy of `len` cells */
+ec_status ec_buf_from_host(uint8_t ct, const void* host, size_t len, ec_buf** out);
+/* with_defaults (:68-77) */
+ec_status ec_buf_with_defaults(size_t len, uint8_t ct, ec_buf** out);
+/* fill (:79-88): type = the value's type */
+ec_status ec_buf_fill(size_t len, const ec_value* value, ec_buf** out);
+/* wrap caller-owned device memory (row strip of a raster already in HBM); not freed by ec_buf_free */
+ec_status ec_buf_wrap_device(uint8_t ct, void* device_ptr, size_t len, ec_buf** out);
+ec_status ec_buf_clone(const ec_buf* b, ec_buf** out);   /* #[derive(Clone)] (:50) */
+void ec_buf_free(ec_buf* b);                             /* Drop */
+size_t ec_buf_len(const ec_buf* b);                      /* :90-99 */
+uint8_t ec_buf_ctype(const ec_buf* b);                   /* :105-114 */
+void* ec_buf_device_ptr(const ec_buf* b);
+/* to_vec's copy-out after convert (:175-185): D2H of len*size_of(ct) bytes, synchronises */
+ec_status ec_buf_to_host(const ec_buf* b, void* host, size_t host_bytes);
+ec_status ec_buf_get(const ec_buf* b, size_t index, ec_value* out);     /* :125-134, EC_OOB = panic */
+ec_status ec_buf_put(ec_buf* b, size_t index, const ec_value* value);   /* :136-148 */
+/* Extend<C> (:205-221): append `n` host cells of type `ct`, converted with `to_<p>().unwrap()`
+ * semantics (EC_NARROWING where the reference would panic) */
+ec_status ec_buf_extend_host(ec_buf* b, uint8_t ct, const void* host, size_t n);
+/* cb_bin_op! `&A op &B` (:324-329): zip => min(len), out Float64 (UInt8 if empty) */
+ec_status ec_buf_binary(int op, const ec_buf* l, const ec_buf* r, ec_buf** out);
+/* cb_bin_op! `A op scalar` (:346-352) */
+ec_status ec_buf_scalar(int op, const ec_buf* l, const ec_value* r, ec_buf** out);
+/* Neg (:360-371) with the per-type widening of src/value.rs:224-240 (signed MIN wraps) */
+ec_status ec_buf_neg(const ec_buf* b, ec_buf** out);
+/* convert (:150-167): same type = clone; illegal = EC_NARROWING before any launch */
+ec_status ec_buf_convert(const ec_buf* b, uint8_t ct, ec_buf** out);
+/* min_max (:169-173); with a mask: MaskedCellBuffer::min_max (src/masked/masked_buffer.rs:208-217).
+ * Total order for floats, seeds (T::MAX, T::MIN) participate. */
+ec_status ec_buf_min_max(const ec_buf* b, const ec_mask* mask_or_null, ec_value* min_out, ec_value* max_out);
+/* Ord/Eq for CellBuffer (:373-436): cell type, then lexicographic total order, then length */
+ec_status ec_buf_cmp(const ec_buf* l, const ec_buf* r, int* ordering);
+
+/* ---- fused op chains behind the same operators ------------------------- */
+/* `(&a - &b) / (&a + &b)` with the three roundings of the unfused chain; 1 pass over HBM */
+ec_status ec_buf_normalized_difference(const ec_buf* a, const ec_buf* b, ec_buf** out);
+/* `(l op1 r) op2 s`, e.g. README `buf1 / buf2 * 0.5` */
+ec_status ec_buf_binary_scalar(int op1, const ec_buf* l, const ec_buf* r, int op2, const ec_value* s, ec_buf** out);
+
+/* ---- Mask — src/masked/mask.rs -------------------------------------------------------------- */
+ec_status ec_mask_from_bools(const uint8_t* host_bools, size_t len, ec_mask** out);  /* Mask::new :16-18 */
+ec_status ec_mask_fill(size_t len, int value, ec_mask** out);                        /* :21-23 */
+ec_status ec_mask_to_bools(const ec_mask* m, uint8_t* host_bools, size_t capacity);  /* IntoIterator :171-177 */
+ec_status ec_mask_clone(const ec_mask* m, ec_mask** out);
+void ec_mask_free(ec_mask* m);
+size_t ec_mask_len(const ec_mask* m);                                               /* :37-39 */
+void* ec_mask_device_words(const ec_mask* m);
+ec_status ec_mask_get(const ec_mask* m, size_t index, int* out);                    /* :58-60 */
+ec_status ec_mask_put(ec_mask* m, size_t index, int value);                         /* :50-52 */
+ec_status ec_mask_extend_host(ec_mask* m, const uint8_t* host_bools, size_t n);     /* Extend :83-87 */
+ec_status ec_mask_not(const ec_mask* m, ec_mask** out);                             /* :103-116 */
+ec_status ec_mask_and(const ec_mask* l, const ec_mask* r, ec_mask** out);           /* :118-140, min(len) */
+ec_status ec_mask_or(const ec_mask* l, const ec_mask* r, ec_mask** out);            /* :142-164 */
+ec_status ec_mask_counts(const ec_mask* m, size_t* data, size_t* nodata);           /* :72-80 */
+ec_status ec_mask_all(const ec_mask* m, int value, int* out);                       /* :67-69 */
+ec_status ec_mask_cmp(const ec_mask* l, const ec_mask* r, int* ordering);           /* derive(Ord) :10 */
+
+/* ---- MaskedCellBuffer / NoData — src/masked/masked_buffer.rs, src/masked/nodata.rs ----------- */
+/* NoData::value (:23-40): returns EC_OK and *has_value = 0 for NoData::None */
+ec_status ec_nodata_value(int kind, uint8_t ct, const ec_value* value_or_null, ec_value* out, int* has_value);
+/* from_vec_with_nodata (:62-71): mask[i] = !(cell[i] == sentinel) under total order (bitwise) */
+ec_status ec_mask_from_nodata(const ec_buf* b, int kind, const ec_value* value_or_null, ec_mask** out);
+/* to_vec_with_nodata (:137-152): convert to dst_ct (EC_NARROWING if illegal) and replace cells whose
+ * mask bit is 0 by the sentinel, one fused pass. kind NONE = plain convert. */
+ec_status ec_buf_fill_nodata(const ec_buf* b, const ec_mask* m, uint8_t dst_ct, int kind,
+                             const ec_value* value_or_null, ec_buf** out);
+/* masked cb_bin_op! (:326-336): data as ec_buf_binary on all cells, mask = lmask & rmask, fused */
+ec_status ec_masked_binary(int op, const ec_buf* lbuf, const ec_mask* lmask, const ec_buf* rbuf,
+                           const ec_mask* rmask, ec_buf** out_buf, ec_mask** out_mask);
+
+/* ---- row-strip sharding across GPUs (no reference counterpart) ----------------- */
+/* Strip `shard` of `n_shards` for a width x height row-major raster: whole rows, remainder rows to
+ * the last shard, and every strip start a multiple of 128 cells (asserted: width % 128 == 0 or
+ * n_shards == 1; otherwise the split falls back to 128-cell aligned cell ranges). */
+ec_status ec_row_strip(size_t width, size_t height, int n_shards, int shard, size_t* cell_offset, size_t* cell_len);
+/* Shard-local part of a reduction: leaves {min_key, ~max_key} as two int64 in device memory so one
+ * MIN all-reduce (NCCL, e.g. torch.distributed or ec_comm_allreduce_min_i64) finishes it. Keys are
+ * order-preserving integers, so the result is bit-identical for every shard count. */
+ec_status ec_buf_min_max_keys(const ec_buf* b, const ec_mask* mask_or_null, int64_t* device_keys2);
+ec_status ec_min_max_from_keys(uint8_t ct, const int64_t* host_keys2, ec_value* min_out, ec_value* max_out);
+/* NCCL communicator over the GPUs of one box, one rank per process (libnccl is dlopen'ed lazily) */
+ec_status ec_comm_unique_id(void* id128);  /* 128 bytes, created on rank 0 and shipped by the host */
+ec_status ec_comm_init_rank(const void* id128, int n_ranks, int rank, ec_comm** out);
+void ec_comm_destroy(ec_comm* c);
+ec_status ec_comm_allreduce_min_i64(ec_comm* c, int64_t* device_buf, size_t count);
+ec_status ec_comm_allreduce_sum_u64(ec_comm* c, uint64_t* device_buf, size_t count);
+/* sharded min_max / counts: shard-local kernel + one all-reduce, result on every rank */
+ec_status ec_buf_min_max_sharded(ec_comm* c, const ec_buf* shard, const ec_mask* mask_or_null,
+                                 ec_value* min_out, ec_value* max_out);
+ec_status ec_mask_counts_sharded(ec_comm* c, const ec_mask* shard, size_t* data, size_t* nodata);
+
+/* ---- synthetic rasters (bench/test utility): counter-based splitmix64(seed ^ index) ----------- */
+/* cell i = f(h), h = splitmix64(seed ^ (index_offset + i)). kind 0: the low bits of h (uniform over
+ * the full bit range of the type, NaN/inf/subnormals included); kind 1: uniform integer in [lo, hi]
+ * cast to the type; kind 2: uniform real lo + u*(hi-lo), u = (h>>11)*2^-53, cast to the type. When
+ * a sentinel is given, cells with splitmix64(h) % period == 0 are replaced by it. Host mirror:
+ * erased_cells_b200/synth.py. */
+ec_status ec_buf_synth(uint8_t ct, size_t len, uint64_t seed, uint64_t index_offset, int kind, double lo,
+                       double hi, uint64_t period, const ec_value* sentinel_or_null, ec_buf** out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ERASED_CELLS_B200_H */

@@ -1,0 +1,143 @@
+"""CPU-side checks of the product: the C-ABI library loads, exports every symbol include/*.h
+declares, its host-side CellType/CellValue logic agrees with the oracle, and device entry points
+fail loudly (no CPU fallback) when no GPU is present. No device compute here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import erased_cells_b200 as ec
+from erased_cells_b200 import CellType, CellValue, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "erased_cells_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ec_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    L = ec.lib()
+    assert L.ec_abi_version() == 1
+    names = declared_symbols()
+    assert len(names) > 80
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in the header but not exported"
+    # and the ctypes table binds exactly the declared set
+    assert sorted(_lib._signatures().keys()) == names
+
+
+def test_value_struct_layout():
+    assert C.sizeof(_lib.Value) == 16 and _lib.Value.bits.offset == 8
+
+
+def test_union_lattice_matches_oracle(orc):
+    for a in CellType:
+        for b in CellType:
+            assert int(a.union(b)) == orc.union(int(a), int(b))
+            assert a.can_fit_into(b) == orc.can_fit_into(int(a), int(b))
+        assert a.size_of() == orc.size_of(int(a))
+        assert a.is_integral() == orc.is_integral(int(a)) and a.is_signed() == orc.is_signed(int(a))
+        assert str(a) == orc.name(int(a)) and CellType.from_str(str(a)) == a
+        for f, g in ((a.min_value, orc.min_value), (a.max_value, orc.max_value), (a.zero, orc.zero), (a.one, orc.one)):
+            v, w = f(), g(int(a))
+            assert (int(v.cell_type()), v.bits) == w.key()
+    with pytest.raises(ec.ParseError):
+        CellType.from_str("UInt57")  # src/ctype.rs:263
+
+
+def _specials(ct, rng):
+    dt = CellType(ct).dtype
+    raw = rng.integers(0, 256, size=64 * dt.itemsize, dtype=np.uint8).view(dt).copy()
+    if dt.kind == "f":
+        raw[:8] = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, -np.nan, 1.5, -2.5], dtype=dt)
+    else:
+        info = np.iinfo(dt)
+        raw[:4] = np.array([info.min, info.max, 0, 1], dtype=dt)
+    return raw
+
+
+def test_scalar_ops_match_oracle(orc):
+    rng = np.random.default_rng(42)
+    for lct in CellType:
+        ls = _specials(lct, rng)
+        for rct in CellType:
+            rs = _specials(rct, rng)
+            for x, y in zip(ls[:24], rs[:24]):
+                a, b = CellValue(lct, x), CellValue(rct, y)
+                oa, ob = orc.value(int(lct), x), orc.value(int(rct), y)
+                for op, got in enumerate((a + b, a - b, a * b, a / b)):
+                    want = orc.value_binary(op, oa, ob)
+                    assert (int(got.cell_type()), got.bits) == want.key(), (lct, rct, op, x, y)
+                assert a.cmp(b) == orc.value_cmp(oa, ob)
+        for x in ls:
+            a, oa = CellValue(lct, x), orc.value(int(lct), x)
+            n, on = -a, orc.value_neg(oa)
+            assert (int(n.cell_type()), n.bits) == on.key()
+            assert a.to_f64() == orc.value_to_f64(oa) or (np.isnan(a.to_f64()) and np.isnan(orc.value_to_f64(oa)))
+            assert a.to_i64() == orc.value_to_i64(oa) and a.to_u64() == orc.value_to_u64(oa)
+            for d in CellType:
+                if lct.can_fit_into(d):
+                    c = a.convert(d)
+                    assert (int(c.cell_type()), c.bits) == orc.value_convert(oa, int(d)).key()
+                else:
+                    with pytest.raises(ec.NarrowingError) as e:
+                        a.convert(d)
+                    assert (e.value.src, e.value.dst) == (int(lct), int(d))
+
+
+def test_reference_scalar_kats():
+    # src/value.rs:313-329, :338-346, :349-391 through the product's host scalar path
+    assert CellValue(CellType.UInt8, 43).convert(CellType.Int16) == CellValue(CellType.Int16, 43)
+    with pytest.raises(ec.NarrowingError):
+        CellValue(CellType.Float32, 3.11111).convert(CellType.Int32)
+    assert CellValue(CellType.UInt16, 33).convert(CellType.Float32).cell_type() == CellType.Float32
+    n = -CellValue(CellType.UInt8, 1)
+    assert n.cell_type() == CellType.Int16 and n.value() == -1
+    l, r = CellValue(CellType.UInt8, 1), CellValue(CellType.UInt8, 2)
+    assert l + r == CellValue(CellType.Float64, 3.0) and l + 2 == CellValue(CellType.Float64, 3.0)
+    assert (l / r).cell_type() == CellType.Float64 and (l / r).value() == 0.5
+    # doc-test src/buffer.rs:36: ((max - min + 1) / 2) == 4.5
+    assert ((CellValue(CellType.UInt8, 8) - CellValue(CellType.UInt8, 0) + 1) / 2) == CellValue.new(4.5)
+
+
+def test_nodata_value_defaults():
+    from erased_cells_b200 import NoData
+    assert NoData.none(CellType.Int16).value() is None
+    assert NoData.default(CellType.UInt8).value() == 0
+    assert np.isnan(NoData.default(CellType.Float32).value())
+    assert NoData.new(CellType.UInt16, 6).value() == 6
+    assert NoData.default(CellType.Int16).value() == -32768
+    assert CellValue.new(np.float64("nan")).is_nodata(NoData.default(CellType.Float64))  # src/masked/nodata.rs:92-94
+
+
+def test_row_strips():
+    L = ec.lib()
+    off, ln = C.c_size_t(), C.c_size_t()
+    cover = 0
+    for g in range(8):
+        assert L.ec_row_strip(32768, 32768, 8, g, C.byref(off), C.byref(ln)) == 0
+        assert off.value == cover and off.value % 128 == 0 and ln.value == 32768 * 4096
+        cover += ln.value
+    assert cover == 32768 * 32768
+    cover = 0
+    for g in range(3):  # ragged: remainder rows go to the last strip; unaligned width falls back to cell ranges
+        assert L.ec_row_strip(186, 169, 3, g, C.byref(off), C.byref(ln)) == 0
+        assert off.value == cover and off.value % 128 == 0
+        cover += ln.value
+    assert cover == 186 * 169
+
+
+def test_device_calls_fail_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(ec.NoDeviceError):
+        ec.CellBuffer.from_vec(np.arange(4, dtype=np.uint8))
+    with pytest.raises(ec.NoDeviceError):
+        ec.Mask.fill(4, True)

@@ -1,0 +1,282 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bit-exact for everything: integer, cast, mask and f64 work (NaN results follow the x86 rule the
+reference's platform produces). Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+import erased_cells_b200 as ec
+from erased_cells_b200 import CellBuffer, CellType, CellValue, Mask, MaskedCellBuffer, NoData, synth
+
+pytestmark = pytest.mark.gpu
+CT = list(CellType)
+# ragged sizes around the tile boundaries (tiles are 256*V*4 cells), plus tiny and empty
+SIZES = [0, 1, 3, 31, 33, 1000, 4096, 4097, 16384 + 5, 3 * 32768 + 77]
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view({1: "u1", 2: "u2", 4: "u4", 8: "u8"}[a.dtype.itemsize])
+
+
+def cells(ct, n, seed):
+    """full-bit-range cells with specials sprinkled in (NaN payloads, infs, zeros, MIN/MAX)"""
+    a = synth.host(ct, n, seed)
+    dt = CellType(ct).dtype
+    if n >= 16:
+        if dt.kind == "f":
+            sp = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, -np.nan, 1.0, -1.0], dtype=dt)
+        else:
+            info = np.iinfo(dt)
+            sp = np.array([info.min, info.max, 0, 1, 0, 0, info.max, info.min], dtype=dt)
+        a = a.copy()
+        a[:: max(n // 8, 1)][:8] = sp[: len(a[:: max(n // 8, 1)][:8])]
+    return a
+
+
+@pytest.mark.parametrize("lct", CT)
+def test_binary_all_pairs(orc, lct):
+    for rct in CT:
+        for n in (0, 5, 4097, 2 * 32768 + 19):
+            l, r = cells(lct, n, 0x100 + int(lct)), cells(rct, n + (3 if n else 0), 0x200 + int(rct))  # zip truncates
+            dl, dr = CellBuffer.from_vec(l), CellBuffer.from_vec(r)
+            for op in range(4):
+                got = dl._bin(op, dr)
+                want = orc.tight_binary(op, l, r)
+                assert got.cell_type() == (CellType.Float64 if n else CellType.UInt8)
+                assert got.len() == n
+                assert np.array_equal(bits(got.to_vec()), bits(want)), (lct, rct, op, n)
+
+
+def test_binary_matches_faithful_oracle_small(orc):
+    # the per-cell tagged flavour (what the reference executes), small sizes
+    for lct in CT:
+        for rct in CT:
+            l, r = cells(lct, 300, 7 + int(lct)), cells(rct, 300, 70 + int(rct))
+            for op in range(4):
+                got = CellBuffer.from_vec(l)._bin(op, CellBuffer.from_vec(r)).to_vec()
+                assert np.array_equal(bits(got), bits(orc.binary(op, l, r))), (lct, rct, op)
+
+
+@pytest.mark.parametrize("lct", CT)
+def test_scalar_all_pairs(orc, lct):
+    for n in (0, 7, 8192 + 3):
+        l = cells(lct, n, 0x300 + int(lct))
+        dl = CellBuffer.from_vec(l)
+        for rct in CT:
+            for s in cells(rct, 16, 0x400 + int(rct))[:6]:
+                for op in range(4):
+                    got = dl._bin(op, CellValue(rct, s))
+                    want = orc.tight_scalar(op, l, orc.value(int(rct), s))
+                    assert got.cell_type() == (CellType.Float64 if n else CellType.UInt8)
+                    assert np.array_equal(bits(got.to_vec()), bits(want)), (lct, rct, op, n, s)
+    # python literals: int -> Int32, float -> Float64 (Rust literal defaults)
+    assert np.array_equal((CellBuffer.from_vec(np.arange(9, dtype=np.uint8)) * 2.0).to_vec(), np.arange(9) * 2.0)
+
+
+def test_neg_all_types(orc):
+    for ct in CT:
+        for n in SIZES:
+            a = cells(ct, n, 0x500 + int(ct))
+            got = -CellBuffer.from_vec(a)
+            want = orc.neg(a)
+            assert got.cell_type().dtype == want.dtype and got.len() == n
+            assert np.array_equal(bits(got.to_vec()), bits(want)), (ct, n)
+
+
+def test_convert_all_pairs(orc):
+    for s in CT:
+        for n in (0, 9, 4097, 32768 + 1):
+            a = cells(s, n, 0x600 + int(s))
+            da = CellBuffer.from_vec(a)
+            for d in CT:
+                if not s.can_fit_into(d):
+                    with pytest.raises(ec.NarrowingError) as e:
+                        da.convert(d)
+                    assert (e.value.src, e.value.dst) == (int(s), int(d))
+                    assert "Invalid narrowing from cell-type" in str(e.value)
+                    continue
+                got = da.convert(d)
+                want = orc.tight_convert(a, int(d))
+                assert got.cell_type().dtype == want.dtype, (s, d, n)  # empty non-identity => UInt8
+                assert np.array_equal(bits(got.to_vec()), bits(want)), (s, d, n)
+                if n:
+                    assert np.array_equal(bits(da.to_vec(d)), bits(want))
+
+
+def test_min_max_all_types(orc):
+    for ct in CT:
+        for n in SIZES + [(1 << 20) + 13]:
+            a = cells(ct, n, 0x700 + int(ct))
+            da = CellBuffer.from_vec(a)
+            mn, mx = da.min_max()
+            omn, omx = orc.tight_min_max(a)
+            assert (int(mn.cell_type()), mn.bits, mx.bits) == (int(ct), omn.bits, omx.bits), (ct, n)
+            m = synth.host(CellType.UInt8, n, 0x800 + n) < 100
+            mmn, mmx = MaskedCellBuffer(da, Mask.new(m)).min_max()
+            omn, omx = orc.tight_min_max(a, m)
+            assert (mmn.bits, mmx.bits) == (omn.bits, omx.bits), (ct, n, "masked")
+    # total order + seeds
+    mn, mx = CellBuffer.from_vec(np.array([np.inf], np.float32)).min_max()
+    assert mn.value() == np.finfo(np.float32).max and mx.value() == np.inf
+    mn, mx = CellBuffer.from_vec(np.array([0.0, -0.0])).min_max()
+    assert (mn.bits, mx.bits) == (0x8000000000000000, 0)
+    mn, mx = MaskedCellBuffer(CellBuffer.from_vec(np.arange(5, dtype=np.int16)), Mask.fill(5, False)).min_max()
+    assert (mn.value(), mx.value()) == (32767, -32768)
+
+
+def test_min_max_finite_values_small_faithful(orc):
+    for ct in CT:
+        a = cells(ct, 999, 0x900 + int(ct))
+        mn, mx = CellBuffer.from_vec(a).min_max()
+        omn, omx = orc.min_max(a)
+        assert (mn.bits, mx.bits) == (omn.bits, omx.bits)
+
+
+def test_mask_ops(orc):
+    for n in SIZES:
+        a = synth.host(CellType.UInt8, n, 0xA00 + n) < 128
+        b = synth.host(CellType.UInt8, n + 5, 0xB00 + n) < 64
+        ma, mb = Mask.new(a), Mask.new(b)
+        assert ma.len() == n and np.array_equal(ma.to_vec(), a)
+        assert np.array_equal((~ma).to_vec(), orc.mask_not(a))
+        assert np.array_equal((ma & mb).to_vec(), orc.mask_and(a, b))
+        assert np.array_equal((ma | mb).to_vec(), orc.mask_or(a, b))
+        assert np.array_equal((mb & ma).to_vec(), orc.mask_and(b, a))
+        assert ma.counts() == orc.mask_counts(a)
+        assert (~ma).counts() == orc.mask_counts(orc.mask_not(a))  # tail bits stay clear
+        assert (mb | ma).counts() == orc.mask_counts(orc.mask_or(b, a))
+        for v in (True, False):
+            assert ma.all(v) == orc.mask_all(a, v)
+        assert Mask.fill(n, True).counts() == (n, 0) and Mask.fill(n, False).counts() == (0, n)
+        assert ma == Mask.new(a) and (n == 0 or ma != ~ma)
+    m = Mask.fill(70, True)
+    m.put(1, False)
+    m[69] = False
+    assert not m.get(1) and not m[69] and m[2] and m.counts() == (68, 2)
+    with pytest.raises(IndexError):
+        m.get(70)
+    m.extend([True, False, True])
+    assert m.len() == 73 and list(m.to_vec()[-3:]) == [True, False, True]
+    # derive(Ord) on Vec<bool>: lexicographic, false < true, then length
+    assert Mask.new([False, True]) < Mask.new([True, False]) and Mask.new([True]) < Mask.new([True, False])
+
+
+def test_from_nodata_and_fill_nodata(orc):
+    for ct in CT:
+        for n in (0, 5, 4096 + 33, 65536 + 7):
+            a = cells(ct, n, 0xC00 + int(ct))
+            if n > 20:  # make sure sentinels occur
+                a[3::17] = a[3]
+            da = CellBuffer.from_vec(a)
+            kinds = [(NoData.default(ct), (orc.ND_DEFAULT, None)), (NoData.none(ct), (orc.ND_NONE, None))]
+            if n:
+                kinds.append((NoData.new(ct, a[3 % n]), (orc.ND_VALUE, orc.value(int(ct), a[3 % n]))))
+            for nd, (ok, ov) in kinds:
+                m = MaskedCellBuffer.from_buffer_with_nodata(da, nd)
+                want = orc.mask_from_nodata(a, ok, ov)
+                assert np.array_equal(m.mask().to_vec(), want), (ct, n, ok)
+                assert m.counts() == orc.mask_counts(want)
+            # to_vec_with_nodata over every legal target type
+            mask = synth.host(CellType.UInt8, n, 0xD00 + n) < 200
+            mb = MaskedCellBuffer(da, Mask.new(mask))
+            for d in CT:
+                fills = [NoData.default(d), NoData.none(d), NoData.new(d, 7)]
+                if not ct.can_fit_into(d):
+                    with pytest.raises(ec.NarrowingError):
+                        mb.to_vec_with_nodata(fills[0])
+                    continue
+                for nd, (ok, ov) in zip(fills, [(orc.ND_DEFAULT, None), (orc.ND_NONE, None), (orc.ND_VALUE, orc.value(int(d), 7))]):
+                    got = mb.to_vec_with_nodata(nd)
+                    want = orc.fill_nodata(a, mask, int(d), ok, ov)
+                    assert got.dtype == want.dtype and np.array_equal(bits(got), bits(want)), (ct, d, n, ok)
+    # bitwise sentinel semantics: only the canonical +qNaN is the float default; Value(0.0) != -0.0
+    a = np.array([0x7FF8000000000000, 0xFFF8000000000000, 0x7FF8000000000001], dtype=np.uint64).view(np.float64)
+    assert list(MaskedCellBuffer.from_vec_with_nodata(a, NoData.default(CellType.Float64)).mask().to_vec()) == [False, True, True]
+    z = np.array([0.0, -0.0])
+    assert list(MaskedCellBuffer.from_vec_with_nodata(z, NoData.new(CellType.Float64, 0.0)).mask().to_vec()) == [False, True]
+
+
+def test_masked_binary_and_chain(orc):
+    for (lct, rct) in [(CellType.Int16, CellType.Int16), (CellType.UInt8, CellType.Float32), (CellType.Float64, CellType.UInt64)]:
+        for n, extra in ((0, 0), (77, 0), (4096 * 3 + 5, 0), (8192 + 40, 9)):
+            l, r = cells(lct, n, 0xE00), cells(rct, n + extra, 0xE01)
+            lm = synth.host(CellType.UInt8, n, 0xE02) < 200
+            rm = synth.host(CellType.UInt8, n + extra, 0xE03) < 220
+            ml = MaskedCellBuffer(CellBuffer.from_vec(l), Mask.new(lm))
+            mr = MaskedCellBuffer(CellBuffer.from_vec(r), Mask.new(rm))
+            for op in range(4):
+                got = ml._bin(op, mr)
+                assert np.array_equal(bits(got.to_vec()), bits(orc.tight_binary(op, l, r))), (lct, rct, op, n)
+                assert np.array_equal(got.mask().to_vec(), orc.mask_and(lm, rm))
+                assert got.counts() == orc.mask_counts(orc.mask_and(lm, rm))
+            s = ml * 0.0001
+            assert np.array_equal(s.mask().to_vec(), lm)
+            assert np.array_equal(bits(s.to_vec()), bits(orc.tight_scalar(orc.MUL, l, orc.value(orc.Float64, 0.0001))))
+            ng = -ml
+            assert np.array_equal(bits(ng.to_vec()), bits(orc.neg(l))) and np.array_equal(ng.mask().to_vec(), lm)
+    with pytest.raises(AssertionError):
+        MaskedCellBuffer(CellBuffer.with_defaults(4, CellType.UInt8), Mask.fill(5, True))
+
+
+def test_fused_chains_equal_unfused(orc):
+    for (lct, rct) in [(CellType.UInt16, CellType.UInt16), (CellType.UInt8, CellType.UInt16), (CellType.Float32, CellType.Int64),
+                       (CellType.Float64, CellType.Float64), (CellType.Int8, CellType.UInt64)]:
+        for n in (0, 100, 32768 + 3):
+            l, r = cells(lct, n, 0xF00), cells(rct, n, 0xF01)
+            if n > 50 and lct == rct:
+                r[5::7] = l[5::7]  # (a-b)/(a+b) with a == b, and 0/0 where both are 0
+                l[10::50] = 0
+                r[10::50] = 0
+            dl, dr = CellBuffer.from_vec(l), CellBuffer.from_vec(r)
+            fused = dl.normalized_difference(dr)
+            unfused = (dl - dr) / (dl + dr)
+            want = orc.tight_binary(orc.DIV, orc.tight_binary(orc.SUB, l, r), orc.tight_binary(orc.ADD, l, r))
+            assert fused == unfused and np.array_equal(bits(fused.to_vec()), bits(want)), (lct, rct, n)
+            for op1 in range(4):
+                for op2 in range(4):
+                    f = dl.binary_scalar(op1, dr, op2, 0.5)
+                    w = orc.tight_scalar(op2, orc.tight_binary(op1, l, r), orc.value(orc.Float64, 0.5))
+                    assert np.array_equal(bits(f.to_vec()), bits(w)), (lct, rct, op1, op2, n)
+
+
+def test_buffer_cmp(orc):
+    for ct in CT:
+        a = cells(ct, 5000, 0x111 + int(ct))
+        da = CellBuffer.from_vec(a)
+        assert da == CellBuffer.from_vec(a) and da.cmp(da.clone()) == 0
+        for pos in (0, 1, 2500, 4999):
+            b = a.copy()
+            bits(b)[pos] ^= 1
+            assert da.cmp(CellBuffer.from_vec(b)) == orc.buffer_cmp(a, b) != 0
+            assert CellBuffer.from_vec(b).cmp(da) == orc.buffer_cmp(b, a)
+        assert da.cmp(CellBuffer.from_vec(a[:-1])) == 1 and CellBuffer.from_vec(a[:-1]).cmp(da) == -1
+    # cell type dominates (src/buffer.rs:395-398)
+    assert CellBuffer.with_defaults(4, CellType.UInt8) < CellBuffer.with_defaults(4, CellType.Float32)
+
+
+def test_get_put_fill_extend(orc):
+    for ct in CT:
+        b = CellBuffer.fill(1000 + int(ct), CellValue(ct, 3))
+        assert b.cell_type() == ct and b.len() == 1000 + int(ct) and np.all(b.to_vec() == 3)
+        b.put(7, ct.one())
+        assert b.get(7) == ct.one() and b.get(8) == CellValue(ct, 3)
+        with pytest.raises(IndexError):
+            b.get(b.len())
+        if ct != CellType.Float64:
+            with pytest.raises(ec.NarrowingError):
+                b.put(0, CellValue(CellType.Float64, 1.0))
+        z = CellBuffer.with_defaults(33, ct)
+        assert np.all(z.to_vec() == 0) and z.get(0) == ct.zero()
+    b = CellBuffer.fill(3, CellValue(CellType.UInt16, 0))
+    b.extend(np.array([1, 2], dtype=np.uint8))
+    assert b.cell_type() == CellType.UInt16 and list(b.to_vec()) == [0, 0, 0, 1, 2]
+
+
+def test_synth_host_equals_device():
+    for ct in CT:
+        for kind, lo, hi in ((synth.FULL_BITS, 0, 0), (synth.INT_RANGE, 0, 100), (synth.REAL_RANGE, -1e4, 1e4)):
+            if kind == synth.INT_RANGE and ct.dtype.kind != "f" and np.iinfo(ct.dtype).min < 0:
+                lo = -50
+            h = synth.host(ct, 10007, 0xEC40, 123, kind, lo, hi, 50, 1)
+            d = synth.device(ct, 10007, 0xEC40, 123, kind, lo, hi, 50, 1).to_vec()
+            assert np.array_equal(bits(h), bits(d)), (ct, kind)
