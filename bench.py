@@ -1,0 +1,453 @@
+#!/usr/bin/env python
+"""bench.py — erased-cells per-cell compute path on B200 (contract: see the task statement).
+
+Workload (BASELINE.json configs[1], the config the metric is quoted on):
+    CellBuffer::convert sweep over all 10x10 CellType pairs on 8192^2-cell buffers
+    (reference src/buffer.rs:150-167): 59 pairs must return NarrowingError without launching, 10 are
+    clones, 31 are cast kernels; algorithmic bytes per cell = size_of(S) + size_of(D).
+One "step" = one pass of the whole sweep. At N GPUs every rank runs the sweep on its own row strip of
+an (N*8192) x 8192 raster (weak scaling; the path shards with no data-path collective). The other
+BASELINE configs are measured once each and reported under "configs" (not the headline value); the
+reductions there finish with an NCCL all-reduce when N > 1.
+
+  python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+  python bench.py --impl reference ...                   # the reference's CPU algorithm (oracle port) on host cores
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SIDE = 8192
+CT_NAMES = ["UInt8", "UInt16", "UInt32", "UInt64", "Int8", "Int16", "Int32", "Int64", "Float32", "Float64"]
+CT_SIZE = [1, 2, 4, 8, 1, 2, 4, 8, 4, 8]
+METRIC = "Gcells/s (CellBuffer ops; HBM GB/s and % of 8 TB/s under roofline)"
+NOMINAL_GBS = 8000.0
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def legal_pairs(can_fit):
+    """dst-major order: consecutive launches read different sources, so a source is re-read only after
+    >= 1 GB of other traffic (inputs + outputs >> the 126 MB L2)."""
+    return [(s, d) for d in range(10) for s in range(10) if can_fit(s, d)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# =================================================================================================
+# reference arm: the reference's CPU algorithm (oracle port: per-cell tagged dispatch) on host cores
+# =================================================================================================
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    orc.build()
+    orc.lib()
+    from erased_cells_b200 import synth  # host generator only (numpy)
+    threads = os.cpu_count() or 1
+    per_thread = 1 << 17  # cells per thread per pair: 41 pairs * 131072 cells ~ 0.3 s per step per core
+    pairs = legal_pairs(orc.can_fit_into)
+    srcs = [[synth.host(ct, per_thread, 0xEC10 + ct, index_offset=t * per_thread) for ct in range(10)] for t in range(threads)]
+
+    def work(t):
+        for s, d in pairs:
+            orc.convert(srcs[t][s], d)
+        for s in range(10):
+            for d in range(10):
+                if not orc.can_fit_into(s, d):
+                    try:
+                        orc.convert(srcs[t][s][:1], d)
+                    except orc.NarrowingError:
+                        pass
+
+    def step():
+        ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    cells = len(pairs) * per_thread * threads
+    value = cells * args.steps / dt / 1e9
+    sample = f"{len(pairs)} legal pairs x {per_thread} cells x {threads} threads per step (same seeds as the GPU workload)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Gcells/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8..f64 casts (integer/f32/f64)", "data": "synthetic",
+        "config": {"workload": "CellBuffer::convert sweep, all 10x10 CellType pairs, 8192^2-cell buffers (bounded sample per step)",
+                   "cells_per_buffer": SIDE * SIDE, "sample_cells_per_pair_per_step": per_thread * threads},
+        "cpu_baseline": {"value": value, "unit": "Gcells/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Gcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference is Rust (no toolchain in this image): timed the C++ restatement oracle/, faithful per-cell tagged path, "
+                "one independent strip per host thread (the reference itself is single-threaded)",
+    }))
+
+
+# =================================================================================================
+# this repo's arm
+# =================================================================================================
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import erased_cells_b200 as ec
+    from erased_cells_b200 import CellBuffer, CellType, Mask, MaskedCellBuffer, NoData, synth
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: erased_cells_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    L = ec.lib()
+    ec._lib.check(L.ec_init(local))
+    ec._lib.check(L.ec_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream)))  # one stream for torch events + our kernels
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    info = ec._lib.DeviceInfo()
+    ec._lib.check(L.ec_device_info_get(C.byref(info)))
+    cells = args.cells
+    pairs = legal_pairs(lambda s, d: CellType(s).can_fit_into(CellType(d)))
+    illegal = [(s, d) for d in range(10) for s in range(10) if not CellType(s).can_fit_into(CellType(d))]
+    pair_bytes = {(s, d): (CT_SIZE[s] + CT_SIZE[d]) * cells for s, d in pairs}
+    step_bytes = sum(pair_bytes.values())
+    # row strip `rank` of the (world*8192) x 8192 raster: seeds per cell type, index offset per strip
+    srcs = [synth.device(CellType(ct), cells, 0xEC10 + ct, index_offset=rank * cells) for ct in range(10)]
+
+    def sweep(events=None):
+        for i, (s, d) in enumerate(pairs):
+            if events is not None:
+                events[i][0].record()
+            out = srcs[s].convert(CellType(d))
+            if events is not None:
+                events[i][1].record()
+            del out
+        for s, d in illegal:
+            try:
+                srcs[s].convert(CellType(d))
+                raise AssertionError("illegal convert did not fail")
+            except ec.NarrowingError:
+                pass
+
+    # ---- device-resident timing (value) ----------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        sweep()
+    barrier()
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in pairs] for _ in range(args.steps)]
+    launches0 = L.ec_kernel_launches()
+    sampler = ClockSampler(local)
+    sampler.start()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for k in range(args.steps):
+        sweep(ev[k])
+    stop.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = L.ec_kernel_launches() - launches0
+    total_ms = max_over_ranks(start.elapsed_time(stop))
+    ms_per_step = total_ms / args.steps
+    value = len(pairs) * cells * world / (ms_per_step * 1e-3) / 1e9
+
+    per_pair, kern_ms_sum = [], 0.0
+    for i, (s, d) in enumerate(pairs):
+        ms = float(np.mean([ev[k][i][0].elapsed_time(ev[k][i][1]) for k in range(args.steps)]))
+        kern_ms_sum += ms
+        per_pair.append({"src": CT_NAMES[s], "dst": CT_NAMES[d], "bytes_per_cell": CT_SIZE[s] + CT_SIZE[d], "ms": round(ms, 4),
+                         "GBps": round(pair_bytes[(s, d)] / (ms * 1e-3) / 1e9, 1), "Gcells_s": round(cells / (ms * 1e-3) / 1e9, 2)})
+    peak, peak_src = measured_peak()
+    achieved = step_bytes / (kern_ms_sum * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per step from the committed ncu capture
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("convert_sweep_dram_bytes_per_step")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": traffic, "peak_source": peak_src, "frac_of_nominal_8TBs": round(achieved / NOMINAL_GBS, 4),
+                "kernel": "map1_kernel<CastF<S,D>> family: 31 casts + 10 clones per step (100% of the step's kernels)",
+                "algorithmic_bytes_per_step": step_bytes, "kernel_ms_per_step": round(kern_ms_sum, 4),
+                "kernel_share_of_step": round(kern_ms_sum / (start.elapsed_time(stop) / args.steps), 4)}
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        def pinned(nbytes):
+            p = C.c_void_p()
+            ec._lib.check(L.ec_host_alloc(nbytes, C.byref(p)))
+            return p, np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(p.value))
+        hsrc, keep = [], []
+        for ct in range(10):
+            p, raw = pinned(cells * CT_SIZE[ct])
+            keep.append(p)
+            a = raw.view(CellType(ct).dtype)
+            srcs[ct].to_vec(out=a)  # same cells as the device-resident run
+            hsrc.append(a)
+        pout, rawout = pinned(cells * 8)
+        h2d = sum(CT_SIZE[s] for s in range(10)) * cells
+        d2h = sum(CT_SIZE[d] for _, d in pairs) * cells
+
+        def e2e_step():
+            chk = 0
+            for s in range(10):
+                buf = CellBuffer.from_vec(hsrc[s])                      # H2D
+                for d in range(10):
+                    if CellType(s).can_fit_into(CellType(d)):
+                        out = buf.convert(CellType(d)).to_vec(out=rawout[: cells * CT_SIZE[d]].view(CellType(d).dtype))  # D2H
+                        chk ^= int(out.view(np.uint8)[-1])
+                    else:
+                        try:
+                            buf.convert(CellType(d))
+                        except ec.NarrowingError:
+                            pass
+            return chk
+
+        e2e_steps = max(2, min(args.steps, 4))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+        e2e = {"value": len(pairs) * cells * world / (e2e_ms * 1e-3) / 1e9, "unit": "Gcells/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps,
+               "pcie_GBps_each_way": [round(h2d / (e2e_ms * 1e-3) / 1e9, 2), round(d2h / (e2e_ms * 1e-3) / 1e9, 2)],
+               "api": "CellBuffer.from_vec(pinned host) -> convert(ct) -> to_vec(pinned host), per rank"}
+        for p in keep + [pout]:
+            L.ec_host_free(p)
+    del srcs
+
+    # ---- the other BASELINE configs, once each (not the headline) -----------------------------------
+    configs = {}
+    if not args.no_configs:
+        configs = other_configs(ec, L, torch, dist, rank, world, barrier, max_over_ranks, peak)
+
+    # ---- CPU baseline beside it (rank 0, N == 1): oracle port on a bounded sample ----------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as orc
+        orc.build()
+        n = 1 << 21
+        hs = [synth.host(CellType(ct), n, 0xEC10 + ct) for ct in range(10)]
+        t = 0.0
+        for s, d in pairs:
+            orc.convert(hs[s], d)
+            t += orc.last_op_seconds()
+        cpu = {"value": len(pairs) * n / t / 1e9, "unit": "Gcells/s", "cores": 1, "kind": "port",
+               "sample": f"first {n} cells of each source buffer, all {len(pairs)} legal pairs, faithful per-cell tagged path "
+                         f"(reference is single-threaded), {t:.1f} s of CPU work", "host_cores_available": os.cpu_count()}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "Gcells/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8..f64 casts (integer/f32/f64)", "data": "synthetic",
+            "config": {"workload": "CellBuffer::convert sweep over all 10x10 CellType pairs (31 casts + 10 clones + 59 NarrowingError) "
+                                   "on 8192^2-cell buffers, one row strip per GPU",
+                       "cells_per_buffer": cells, "legal_pairs": len(pairs), "l2": "inputs+outputs of a step (%.1f GB) >> %d MB L2; "
+                       "dst-major order, a source is re-read after >= 1 GB of other traffic" % (step_bytes / 1e9, info.l2_bytes >> 20),
+                       "device": info.name.decode(), "sm_count": info.sm_count},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "GBps_algorithmic_step": round(step_bytes * world / (ms_per_step * 1e-3) / 1e9, 1),
+            "per_pair": per_pair, "configs": configs,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def other_configs(ec, L, torch, dist, rank, world, barrier, max_over_ranks, peak):
+    """BASELINE configs 1, 3, 4, 5: a few timed iterations each, CUDA events, buffers >> L2 or rotated."""
+    from erased_cells_b200 import CellBuffer, CellType, MaskedCellBuffer, NoData, synth
+    res = {}
+
+    def timed(fn, iters=5, warm=2):
+        for _ in range(warm):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b)) / iters
+
+    def entry(ms, nbytes, ncells, **kw):
+        g = nbytes / (ms * 1e-3) / 1e9
+        return dict(ms=round(ms, 4), GBps=round(g, 1), Gcells_s=round(ncells / (ms * 1e-3) / 1e9, 2), frac_of_measured=round(g / peak, 3),
+                    frac_of_8TBs=round(g / NOMINAL_GBS, 3), **kw)
+
+    # config 1: u8 4096^2 / u16 4096^2 * 0.5 -> f64; 8 rotating buffer sets so inputs are not L2-resident
+    n1 = 4096 * 4096
+    sets = [(synth.device(CellType.UInt8, n1, 0xEC01 + 16 * i, kind=synth.INT_RANGE, lo=0, hi=255),
+             synth.device(CellType.UInt16, n1, 0xEC02 + 16 * i, kind=synth.INT_RANGE, lo=0, hi=65535)) for i in range(8)]
+    it = [0]
+
+    def c1_unfused():
+        a, b = sets[it[0] % 8]; it[0] += 1
+        return a / b * 0.5
+
+    def c1_div():
+        a, b = sets[it[0] % 8]; it[0] += 1
+        return a / b
+
+    def c1_fused():
+        a, b = sets[it[0] % 8]; it[0] += 1
+        return a.binary_scalar(ec.DIV, b, ec.MUL, 0.5)
+    res["c1_readme_4096"] = {"div_u8_u16": entry(timed(c1_div, 16), 11 * n1, n1), "div_then_mul_unfused": entry(timed(c1_unfused, 16), 27 * n1, n1),
+                             "div_mul_fused": entry(timed(c1_fused, 16), 11 * n1, n1), "scaling": "weak (same buffers on every rank)"}
+    del sets
+
+    # config 3: masked i16 16384^2 with NoData: (a - b) * s, min_max, counts
+    n3 = 16384 * 16384
+    a = synth.device(CellType.Int16, n3, 0xEC31, index_offset=rank * n3, kind=synth.INT_RANGE, lo=-32768, hi=32767, period=50, sentinel=-32768)
+    b = synth.device(CellType.Int16, n3, 0xEC32, index_offset=rank * n3, kind=synth.INT_RANGE, lo=-32768, hi=32767, period=50, sentinel=-32768)
+    nd = NoData.default(CellType.Int16)
+    c3 = {"from_nodata_i16": entry(timed(lambda: MaskedCellBuffer.from_buffer_with_nodata(a, nd)), 2.125 * n3, n3)}
+    ma, mb = MaskedCellBuffer.from_buffer_with_nodata(a, nd), MaskedCellBuffer.from_buffer_with_nodata(b, nd)
+    c3["masked_sub_i16_i16"] = entry(timed(lambda: ma - mb), 12.375 * n3, n3)
+    r = ma - mb
+    c3["masked_mul_scalar_f64"] = entry(timed(lambda: r * 0.0001), 16.0 * n3, n3, note="buffer kernel only; the mask is cloned (1/4 B/cell more)")
+    rs = r * 0.0001
+    c3["masked_min_max_f64"] = entry(timed(lambda: rs.min_max()), 8.125 * n3, n3, note="includes the 16-byte D2H + stream sync of the result")
+    c3["counts"] = entry(timed(lambda: rs.counts()), 0.125 * n3, n3)
+    res["c3_masked_i16_16384"] = c3
+    del a, b, ma, mb, r, rs
+
+    # config 4: f32 32768^2 min_max, row strips over the ranks (strong scaling) + one NCCL all-reduce of 16 bytes
+    n4 = 32768 * 32768
+    off, ln = C.c_size_t(), C.c_size_t()
+    ec._lib.check(L.ec_row_strip(32768, 32768, world, rank, C.byref(off), C.byref(ln)))
+    strip = synth.device(CellType.Float32, ln.value, 0xEC40, index_offset=off.value, kind=synth.REAL_RANGE, lo=-1e4, hi=1e4)
+    keys = torch.empty(2, dtype=torch.int64, device="cuda")
+    hkeys = torch.empty(2, dtype=torch.int64).pin_memory()
+
+    def c4():
+        ec._lib.check(L.ec_buf_min_max_keys(strip._h, None, C.c_void_p(keys.data_ptr())))
+        if world > 1:
+            dist.all_reduce(keys, op=dist.ReduceOp.MIN)
+        hkeys.copy_(keys, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        mn, mx = ec._lib.Value(), ec._lib.Value()
+        ec._lib.check(L.ec_min_max_from_keys(int(CellType.Float32), hkeys.numpy().ctypes.data_as(C.POINTER(C.c_int64)), C.byref(mn), C.byref(mx)))
+        return mn.bits, mx.bits
+    ms4 = timed(c4, 10)
+    res["c4_f32_32768_min_max_sharded"] = entry(ms4, 4.0 * n4, n4, scaling="strong", shards=world, result_bits=[hex(x) for x in c4()],
+                                                note="shard kernel + all-reduce(MIN, 2 x int64) + D2H of the result, host-visible")
+    del strip
+
+    # config 5: NDVI (nir - red) / (nir + red), u16 32768^2 -> f64, one tile per GPU (weak)
+    n5 = 32768 * 32768
+    nir = synth.device(CellType.UInt16, n5, 0xEC50 + rank, kind=synth.INT_RANGE, lo=5000, hi=40000, period=1000, sentinel=0)
+    red = synth.device(CellType.UInt16, n5, 0xEC58 + rank, kind=synth.INT_RANGE, lo=5000, hi=40000, period=1000, sentinel=0)
+    res["c5_ndvi_u16_32768_per_gpu_tile"] = {
+        "unfused_3_ops": entry(timed(lambda: (nir - red) / (nir + red), 3, 1), 48.0 * n5, n5),
+        "fused_1_pass": entry(timed(lambda: nir.normalized_difference(red), 3, 1), 12.0 * n5, n5),
+        "scaling": "weak (one tile per GPU)"}
+    nd5 = nir.normalized_difference(red)
+    res["c5_ndvi_u16_32768_per_gpu_tile"]["min_max_f64"] = entry(timed(lambda: nd5.min_max(), 3, 1), 8.0 * n5, n5)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=SIDE * SIDE)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -148,6 +148,7 @@ def _signatures():
         "ec_row_strip": (S, [SZ, SZ, I, I, PSZ, PSZ]),
         "ec_buf_min_max_keys": (S, [VP, VP, VP]),
         "ec_min_max_from_keys": (S, [U8, C.POINTER(I64), PV, PV]),
+        "ec_min_max_to_keys": (S, [PV, PV, C.POINTER(I64)]),
         "ec_comm_unique_id": (S, [VP]),
         "ec_comm_init_rank": (S, [VP, I, I, PVP]),
         "ec_comm_destroy": (None, [VP]),

@@ -597,7 +597,10 @@ ec_status ec_buf_clone(const ec_buf* b, ec_buf** out) {
     EC_TRY(ensure());
     ec_buf* c;
     EC_TRY(new_buf(b->ct, b->len, &c));
-    if (b->len) EC_CUDA_TRY(cudaMemcpyAsync(c->dptr, b->dptr, b->len * kSize[b->ct], cudaMemcpyDeviceToDevice, cur_stream()), "cudaMemcpyAsync(D2D)");
+    if (b->len) {
+        if (cudaError_t e = launch_copy(launch_ctx(), (int)kSize[b->ct], b->dptr, c->dptr, b->len)) { ec_buf_free(c); return cuda_fail(e, "clone"); }
+        note_launch("clone");
+    }
     *out = c;
     return EC_OK;
 }
@@ -1059,6 +1062,13 @@ ec_status ec_min_max_from_keys(uint8_t ct, const int64_t* k, ec_value* mn, ec_va
     if (!ct_ok(ct)) return invalid("cell type");
     *mn = tagged<uint64_t>(ct, key_to_bits(ct, key_from_signed(k[0])));
     *mx = tagged<uint64_t>(ct, key_to_bits(ct, key_from_signed(~k[1])));
+    return EC_OK;
+}
+
+ec_status ec_min_max_to_keys(const ec_value* mn, const ec_value* mx, int64_t* k) {
+    if (!ct_ok(mn->ct) || mn->ct != mx->ct) return invalid("cell type");
+    k[0] = key_to_signed(key_from_bits(mn->ct, mn->bits));
+    k[1] = ~key_to_signed(key_from_bits(mx->ct, mx->bits));
     return EC_OK;
 }
 

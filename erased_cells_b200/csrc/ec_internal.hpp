@@ -54,6 +54,7 @@ cudaError_t launch_binary(const Launch& L, int op, int lct, const void* l, int r
 cudaError_t launch_scalar(const Launch& L, int op, int lct, const void* l, double s, double* out, size_t n);
 cudaError_t launch_neg(const Launch& L, int ct, const void* a, void* out, size_t n);
 cudaError_t launch_convert(const Launch& L, int sct, const void* a, int dct, void* out, size_t n);
+cudaError_t launch_copy(const Launch& L, int cell_bytes, const void* a, void* out, size_t n);
 cudaError_t launch_fill(const Launch& L, int ct, void* out, size_t n, uint64_t bits);
 cudaError_t launch_fill_nodata(const Launch& L, int sct, const void* a, const uint32_t* m, int dct, void* out,
                                size_t n, uint64_t nodata_bits);
@@ -77,6 +78,7 @@ cudaError_t launch_synth(const Launch& L, int ct, void* out, size_t n, uint64_t 
 // keys <-> values on the host (same functions the kernels use)
 void key_seeds(int ct, uint64_t* seed_min, uint64_t* seed_max);
 uint64_t key_to_bits(int ct, uint64_t key);
+uint64_t key_from_bits(int ct, uint64_t bits);
 int64_t key_to_signed(uint64_t key);    // order-preserving int64 for NCCL min/max
 uint64_t key_from_signed(int64_t skey);
 

@@ -13,23 +13,36 @@
 
 namespace ec {
 
-static int reduce_grid(size_t n, size_t tile, const Launch& Lc) {
+// Geometry picked from the tools/ubench sweep on B200 (profiles/r01_ubench_sweep.md): unmasked
+// min_max runs best with 512-thread CTAs, 4 x 32-byte loads in flight per thread and a grid of up to
+// 32 CTAs per SM (6.86-6.97 TB/s for f32/u8/i16/f64); the masked flavour with 2 loads in flight and
+// 8 CTAs per SM (6.77 TB/s).
+constexpr int kRedThreads = 512;
+constexpr int kRedUnroll = 4;
+constexpr int kRedUnrollMasked = 2;
+constexpr size_t kMaxReduceBlocks = 8192;  // size of ReduceScratch::partials (pairs), see ec_api.cu
+
+static int reduce_grid(size_t n, size_t tile, const Launch& Lc, int ctas_per_sm = 32) {
     size_t full = n / tile;
     if (full == 0) full = 1;
-    const size_t cap = size_t(Lc.sm_count) * 8;  // partials array is sized for this
+    size_t cap = size_t(Lc.sm_count) * ctas_per_sm;
+    if (cap > kMaxReduceBlocks) cap = kMaxReduceBlocks;
     return int(full < cap ? full : cap);
 }
 
 template <class T>
 static cudaError_t min_max_t(const Launch& Lc, const void* a, const uint32_t* mask, size_t n, const ReduceScratch& s) {
     constexpr int V = EC_VB / sizeof(T);
-    constexpr size_t TILE = size_t(kThreads) * V * EC_RUNROLL;
     const okey_t<T> smin = to_key<T>(std::numeric_limits<T>::max()), smax = to_key<T>(std::numeric_limits<T>::lowest());
-    const int grid = reduce_grid(n, TILE, Lc);
-    if (mask)
-        min_max_kernel<T, true, EC_VB, EC_RUNROLL, kThreads><<<grid, kThreads, 0, Lc.stream>>>(static_cast<const T*>(a), mask, n, smin, smax, s);
-    else
-        min_max_kernel<T, false, EC_VB, EC_RUNROLL, kThreads><<<grid, kThreads, 0, Lc.stream>>>(static_cast<const T*>(a), nullptr, n, smin, smax, s);
+    if (mask) {
+        constexpr size_t TILE = size_t(kRedThreads) * V * kRedUnrollMasked;
+        min_max_kernel<T, true, EC_VB, kRedUnrollMasked, kRedThreads><<<reduce_grid(n, TILE, Lc, 8), kRedThreads, 0, Lc.stream>>>(
+            static_cast<const T*>(a), mask, n, smin, smax, s);
+    } else {
+        constexpr size_t TILE = size_t(kRedThreads) * V * kRedUnroll;
+        min_max_kernel<T, false, EC_VB, kRedUnroll, kRedThreads><<<reduce_grid(n, TILE, Lc, 32), kRedThreads, 0, Lc.stream>>>(
+            static_cast<const T*>(a), nullptr, n, smin, smax, s);
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_min_max(const Launch& Lc, int ct, const void* a, const uint32_t* mask, size_t n, const ReduceScratch& s) {
@@ -50,6 +63,14 @@ void key_seeds(int ct, uint64_t* seed_min, uint64_t* seed_max) {
 uint64_t key_to_bits(int ct, uint64_t key) {
     switch (ct) {
 #define X(id, p) case id: return static_cast<uint64_t>(to_bits<p>(from_key<p>(static_cast<okey_t<p>>(key))));
+        EC_WITH_CT(X)
+#undef X
+    }
+    return 0;
+}
+uint64_t key_from_bits(int ct, uint64_t bits) {
+    switch (ct) {
+#define X(id, p) case id: return static_cast<uint64_t>(to_key<p>(from_bits<p>(static_cast<bits_t<p>>(bits))));
         EC_WITH_CT(X)
 #undef X
     }

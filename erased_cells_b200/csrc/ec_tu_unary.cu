@@ -59,6 +59,17 @@ cudaError_t launch_convert(const Launch& Lc, int sct, const void* a, int dct, vo
     return cudaErrorInvalidValue;
 }
 
+// Clone / identity convert (src/buffer.rs:50, :151-153): the same streaming kernel with an identity
+// functor on the cell's unsigned carrier (measured faster than the runtime's D2D memcpy on B200).
+cudaError_t launch_copy(const Launch& Lc, int cell_bytes, const void* a, void* out, size_t n) {
+    switch (cell_bytes) {
+        case 1: return go1(Lc, static_cast<const uint8_t*>(a), static_cast<uint8_t*>(out), n, CastF<uint8_t, uint8_t>{});
+        case 2: return go1(Lc, static_cast<const uint16_t*>(a), static_cast<uint16_t*>(out), n, CastF<uint16_t, uint16_t>{});
+        case 4: return go1(Lc, static_cast<const uint32_t*>(a), static_cast<uint32_t*>(out), n, CastF<uint32_t, uint32_t>{});
+        default: return go1(Lc, static_cast<const uint64_t*>(a), static_cast<uint64_t*>(out), n, CastF<uint64_t, uint64_t>{});
+    }
+}
+
 template <class U> static cudaError_t fill_u(const Launch& Lc, void* out, size_t n, uint64_t bits) {
     constexpr size_t TILE = size_t(kThreads) * (EC_VB / sizeof(U));
     fill_kernel<U, EC_VB, kThreads><<<grid_for(n, TILE, Lc), kThreads, 0, Lc.stream>>>(static_cast<U*>(out), n, static_cast<U>(bits));

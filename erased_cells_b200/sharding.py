@@ -1,0 +1,63 @@
+"""Row-strip sharding of one raster across the GPUs of a box (one process per GPU).
+
+Element-wise ops are shard-local: a rank simply holds the CellBuffer / MaskedCellBuffer of its strip.
+Only reductions cross GPUs, and only as 16 bytes: the shard kernel leaves {skey(min), ~skey(max)} in
+device memory and ONE all-reduce(MIN) over int64 finishes both (order-preserving integer keys make the
+result independent of the shard count). The collective is torch.distributed (NCCL over NVLink on the
+GPU box; gloo in the CPU tests); the C ABI also carries its own NCCL communicator (ec_comm_*) for hosts
+without torch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import Value, check, lib
+from .api import CellBuffer, CellType, CellValue, Mask
+
+
+def row_strip(width: int, height: int, n_shards: int, shard: int) -> tuple[int, int]:
+    """(cell_offset, cell_len) of strip `shard`: whole rows, remainder to the last strip, starts on 128-cell boundaries."""
+    off, ln = C.c_size_t(), C.c_size_t()
+    check(lib().ec_row_strip(width, height, n_shards, shard, C.byref(off), C.byref(ln)))
+    return off.value, ln.value
+
+
+def keys_of(mn: CellValue, mx: CellValue) -> np.ndarray:
+    k = np.zeros(2, dtype=np.int64)
+    check(lib().ec_min_max_to_keys(C.byref(mn._v), C.byref(mx._v), k.ctypes.data_as(C.POINTER(C.c_int64))))
+    return k
+
+
+def values_of(ct: CellType, keys) -> tuple[CellValue, CellValue]:
+    k = np.ascontiguousarray(np.asarray(keys, dtype=np.int64))
+    mn, mx = Value(), Value()
+    check(lib().ec_min_max_from_keys(int(ct), k.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(mn), C.byref(mx)))
+    return CellValue._wrap(mn), CellValue._wrap(mx)
+
+
+def finish_min_max(ct: CellType, keys, group=None) -> tuple[CellValue, CellValue]:
+    """all-reduce(MIN) of the packed keys tensor (int64[2], on the device the backend needs) + decode."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
+    return values_of(ct, keys.cpu().numpy())
+
+
+def min_max_sharded(shard: CellBuffer, mask: Mask | None = None, group=None) -> tuple[CellValue, CellValue]:
+    """min_max of the whole raster from this rank's strip (every rank gets the result)."""
+    import torch
+    keys = torch.empty(2, dtype=torch.int64, device="cuda")
+    check(lib().ec_buf_min_max_keys(shard._h, mask._h if mask is not None else None, C.c_void_p(keys.data_ptr())))
+    check(lib().ec_synchronize())
+    return finish_min_max(shard.cell_type(), keys, group)
+
+
+def counts_sharded(mask: Mask, group=None) -> tuple[int, int]:
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(mask.counts()), dtype=torch.int64, device="cuda" if torch.cuda.is_available() else "cpu")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return int(t[0]), int(t[1])

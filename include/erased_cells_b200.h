@@ -218,6 +218,8 @@ ec_status ec_row_strip(size_t width, size_t height, int n_shards, int shard, siz
  * order-preserving integers, so the result is bit-identical for every shard count. */
 ec_status ec_buf_min_max_keys(const ec_buf* b, const ec_mask* mask_or_null, int64_t* device_keys2);
 ec_status ec_min_max_from_keys(uint8_t ct, const int64_t* host_keys2, ec_value* min_out, ec_value* max_out);
+/* inverse of the above (host): pack a partial (min, max) of cell type ct as {skey(min), ~skey(max)} */
+ec_status ec_min_max_to_keys(const ec_value* min_in, const ec_value* max_in, int64_t* host_keys2);
 /* NCCL communicator over the GPUs of one box, one rank per process (libnccl is dlopen'ed lazily) */
 ec_status ec_comm_unique_id(void* id128);  /* 128 bytes, created on rank 0 and shipped by the host */
 ec_status ec_comm_init_rank(const void* id128, int n_ranks, int rank, ec_comm** out);
