@@ -1,0 +1,24 @@
+"""Runs the C++ port of the reference's own tests (tests/cpp/test_reference_port.cpp) — the host
+mirror include/erased_cells.hpp over the C ABI — on the GPU box."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+def test_cpp_reference_port():
+    exe = os.path.join(ROOT, "tests", "cpp", "build", "test_reference_port")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "-s"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert " 0 failed" in r.stdout
+
+
+def test_cpp_port_builds_on_cpu():
+    """the host mirror compiles and links against the C ABI without a GPU"""
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "-s"], check=True)
+    assert os.path.exists(os.path.join(ROOT, "tests", "cpp", "build", "test_reference_port"))
