@@ -55,7 +55,8 @@ def legal_pairs(can_fit):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML polled from a thread (the timed
+    region is tens of ms, too short for nvidia-smi -lms), nvidia-smi as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -63,6 +64,18 @@ class ClockSampler:
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.samples, self.reason_bits, self.run = [], 0, True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
@@ -70,11 +83,37 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        while self.run:
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.001)
+
+    def _stop_nvml(self):
+        nv = self.nvml
+        self.run = False
+        self.thread.join(1.0)
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+        sm = [s[0] for s in self.samples]
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "power_w_max": max([s[1] for s in self.samples], default=None),
+                "samples": len(sm), "reasons": sorted(n for b, n in names.items() if self.reason_bits & b), "source": "nvml"}
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            return self._stop_nvml()
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.05)
@@ -167,7 +206,13 @@ def run_ours(args):
     torch.cuda.set_device(local)
     L = ec.lib()
     ec._lib.check(L.ec_init(local))
-    ec._lib.check(L.ec_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream)))  # one stream for torch events + our kernels
+    # One explicit (non-default) stream for torch events, NCCL collectives and this library's kernels.
+    # (torch's default stream has handle 0, which ec_set_stream reads as "use the library's own stream".)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ec._lib.check(L.ec_set_stream(C.c_void_p(stream.cuda_stream)))
+    assert L.ec_get_stream() == stream.cuda_stream
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 

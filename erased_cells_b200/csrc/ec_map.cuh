@@ -83,8 +83,15 @@ __global__ void __launch_bounds__(THREADS) map1_kernel(const typename F::A* __re
 // ---- two-input map, optionally carrying the validity mask (packed words) along ---------------------
 // When lm != nullptr the CTA that owns a tile also ANDs the tile's mask words (32 cells per word):
 // MaskedCellBuffer op (src/masked/masked_buffer.rs:326-336) in one launch.
+// Register budget: with narrow operands (<= 8 input bytes per cell) the loads in flight are small, so the
+// kernel is held to 64 registers (>= 1024 resident threads per SM) — the f64 division path otherwise drifts
+// to 66 registers = 3 CTAs/SM in the fused functors (ncu, profiles/). Wide operands keep UNROLL x 32 bytes
+// per operand in registers and get the 128-register budget instead.
+template <class F> constexpr int map2_min_ctas(int threads) {
+    return (sizeof(typename F::A) + sizeof(typename F::B) <= 8 ? 1024 : 512) / threads;
+}
 template <class F, int VB, int UNROLL, int THREADS>
-__global__ void __launch_bounds__(THREADS) map2_kernel(const typename F::A* __restrict__ a,
+__global__ void __launch_bounds__(THREADS, map2_min_ctas<F>(THREADS)) map2_kernel(const typename F::A* __restrict__ a,
                                                        const typename F::B* __restrict__ b,
                                                        typename F::O* __restrict__ o, size_t n, F f,
                                                        const uint32_t* __restrict__ lm,
