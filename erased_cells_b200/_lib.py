@@ -76,6 +76,8 @@ def _signatures():
         "ec_set_stream": (S, [VP]),
         "ec_get_stream": (VP, []),
         "ec_synchronize": (S, []),
+        "ec_trim": (S, []),
+        "ec_cached_bytes": (SZ, []),
         "ec_kernel_launches": (U64, []),
         "ec_last_kernel": (C.c_char_p, []),
         "ec_event_create": (S, [PVP]),

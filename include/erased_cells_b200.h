@@ -101,6 +101,10 @@ ec_status ec_device_info_get(ec_device_info* out);
 ec_status ec_set_stream(void* cuda_stream); /* NULL restores the library's own stream */
 void* ec_get_stream(void);
 ec_status ec_synchronize(void);
+/* Freed device blocks are cached per stream for reuse (outputs are fresh allocations on every op).
+ * ec_trim() synchronises the current stream and returns all cached blocks to the driver. */
+ec_status ec_trim(void);
+size_t ec_cached_bytes(void);
 uint64_t ec_kernel_launches(void);       /* number of this library's kernels launched so far */
 /* name of the last kernel family launched by this thread (for profiles/bench bookkeeping) */
 const char* ec_last_kernel(void);

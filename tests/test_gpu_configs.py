@@ -60,9 +60,11 @@ def test_config2_convert_sweep_8192(orc):
             assert out.cell_type() == d and out.len() == n
             # widening is transitive: S -> D -> f64 == S -> f64 (device-side compare, no D2H)
             assert out.convert(T.Float64) == as_f64, (s, d)
-            # widening is monotone under total order: min_max commutes with convert
-            dmn, dmx = out.min_max()
-            assert (dmn.bits, dmx.bits) == (smn.convert(d).bits, smx.convert(d).bits), (s, d)
+            # widening is monotone under total order, so min_max commutes with convert — except f32 -> f64 on
+            # full-bit-range data, where quieting a signalling NaN can lift it above a quiet one
+            if not (s == T.Float32 and d == T.Float64):
+                dmn, dmx = out.min_max()
+                assert (dmn.bits, dmx.bits) == (smn.convert(d).bits, smx.convert(d).bits), (s, d)
             for off in offsets(n)[:2]:
                 hw = synth.host(s, WIN, 0xEC10 + int(s), index_offset=off)
                 assert np.array_equal(bits(window(out, off, WIN)), bits(orc.tight_convert(hw, int(d)))), (s, d, off)
@@ -152,7 +154,9 @@ def test_config5_ndvi_u16_32768_tile(orc):
     fmn, fmx = fused.min_max()
     assert (fmn.bits, fmx.bits) == tuple(v.bits for v in unfused.min_max())
     del unfused
-    assert float(fmn.value()) == -1.0 and float(fmx.value()) == 1.0  # x/0 rows: (0-r)/(0+r), (n-0)/(n+0)
+    # ~0.1 % zeros per band: (0-r)/(0+r) = -1, (n-0)/(n+0) = 1, and where both are 0 the 0/0 is the x86 default
+    # NaN, which is NEGATIVE and therefore the minimum under total order (SURVEY.md §7 risk 2)
+    assert fmn.bits == 0xFFF8000000000000 and float(fmx.value()) == 1.0
     for off in offsets(n):
         hn, hr = synth.host(T.UInt16, WIN, 0xEC50, index_offset=off, **kw), synth.host(T.UInt16, WIN, 0xEC58, index_offset=off, **kw)
         want = orc.tight_binary(orc.DIV, orc.tight_binary(orc.SUB, hn, hr), orc.tight_binary(orc.ADD, hn, hr))
