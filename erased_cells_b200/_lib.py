@@ -107,6 +107,8 @@ def _signatures():
         "ec_value_to_i64": (S, [PV, C.POINTER(I64), PI]),
         "ec_value_to_u64": (S, [PV, C.POINTER(U64), PI]),
         "ec_buf_from_host": (S, [U8, VP, SZ, PVP]),
+        "ec_buf_from_host_async": (S, [U8, VP, SZ, PVP]),
+        "ec_buf_wait": (S, [VP]),
         "ec_buf_with_defaults": (S, [SZ, U8, PVP]),
         "ec_buf_fill": (S, [SZ, PV, PVP]),
         "ec_buf_wrap_device": (S, [U8, VP, SZ, PVP]),

@@ -218,10 +218,11 @@ def _host(a, ct=None) -> np.ndarray:
 
 
 class CellBuffer:
-    __slots__ = ("_h",)
+    __slots__ = ("_h", "_keep")
 
     def __init__(self, handle):
         self._h = handle
+        self._keep = None  # host array of an upload still in flight (from_vec(..., wait=False))
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -238,14 +239,27 @@ class CellBuffer:
         return CellBuffer.from_vec(data)
 
     @staticmethod
-    def from_vec(data) -> "CellBuffer":
-        """from_vec / From<Vec<T>> (src/buffer.rs:64-66, :252-263): one H2D copy."""
+    def from_vec(data, wait: bool = True) -> "CellBuffer":
+        """from_vec / From<Vec<T>> (src/buffer.rs:64-66, :252-263): one H2D copy.
+
+        wait=False returns at once: the copy runs on the upload stream (overlapping D2H traffic) and the
+        buffer keeps `data` alive until it lands — the analogue of from_vec taking ownership of the Vec."""
         a = _host(data)
         ct = CellType.of(a)
         h = C.c_void_p()
-        check(lib().ec_buf_from_host(int(ct), a.ctypes.data_as(C.c_void_p), a.size, C.byref(h)))
-        check(lib().ec_synchronize())  # `a` may be a temporary
-        return CellBuffer._take(h)
+        if wait:
+            check(lib().ec_buf_from_host(int(ct), a.ctypes.data_as(C.c_void_p), a.size, C.byref(h)))
+            check(lib().ec_synchronize())  # `a` may be a temporary
+            return CellBuffer._take(h)
+        check(lib().ec_buf_from_host_async(int(ct), a.ctypes.data_as(C.c_void_p), a.size, C.byref(h)))
+        b = CellBuffer._take(h)
+        b._keep = a
+        return b
+
+    def wait(self) -> "CellBuffer":
+        check(lib().ec_buf_wait(self._h))
+        self._keep = None
+        return self
 
     @staticmethod
     def with_defaults(len_: int, ct: CellType) -> "CellBuffer":

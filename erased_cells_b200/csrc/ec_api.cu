@@ -65,6 +65,7 @@ struct Ctx {
     bool inited = false;
     int device = -1;
     cudaStream_t own = nullptr;
+    cudaStream_t upload = nullptr;  // H2D of ec_buf_from_host_async: overlaps the D2H traffic of the compute stream
     cudaDeviceProp prop;
     int max_grid = 0;
 };
@@ -92,6 +93,12 @@ static ec_status ensure() {
     return EC_OK;
 }
 static cudaStream_t cur_stream() { return t_stream_set ? t_stream : g_ctx.own; }
+// device pointer of a buffer about to be read or written on the current stream: orders the access after an
+// asynchronous upload that may still be in flight on the upload stream
+static inline void* rd(const ec_buf* b) {
+    if (b->ready) cudaStreamWaitEvent(cur_stream(), b->ready, 0);
+    return b->dptr;
+}
 static Launch launch_ctx() { return Launch{cur_stream(), g_ctx.prop.multiProcessorCount, g_ctx.max_grid}; }
 
 // ---- device memory: a stream-keyed caching allocator --------------------------------------------
@@ -407,7 +414,7 @@ cudaError_t launch_binary_scalar(const Launch& L, int op1, int lct, const void* 
 // reduce a buffer to {min_key, max_key} (device, in scratch.result)
 static ec_status run_min_max(const ec_buf* b, const ec_mask* m, ReduceScratch* sc) {
     EC_TRY(reduce_scratch(sc));
-    EC_LAUNCH(launch_min_max(launch_ctx(), b->ct, b->dptr, m ? m->words : nullptr, b->len, *sc), "min_max");
+    EC_LAUNCH(launch_min_max(launch_ctx(), b->ct, rd(b), m ? m->words : nullptr, b->len, *sc), "min_max");
     return EC_OK;
 }
 
@@ -440,6 +447,7 @@ ec_status ec_init(int device) {
     EC_CUDA_TRY(cudaSetDevice(device), "cudaSetDevice");
     EC_CUDA_TRY(cudaGetDeviceProperties(&g_ctx.prop, device), "cudaGetDeviceProperties");
     EC_CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.own, cudaStreamNonBlocking), "cudaStreamCreate");
+    EC_CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.upload, cudaStreamNonBlocking), "cudaStreamCreate");
     g_ctx.max_grid = env_int("EC_MAX_GRID", 0);
     g_ctx.device = device;
     g_ctx.inited = true;
@@ -620,6 +628,29 @@ ec_status ec_buf_from_host(uint8_t ct, const void* host, size_t len, ec_buf** ou
     *out = b;
     return EC_OK;
 }
+ec_status ec_buf_from_host_async(uint8_t ct, const void* host, size_t len, ec_buf** out) {
+    EC_TRY(ensure());
+    if (!ct_ok(ct)) return invalid("cell type");
+    ec_buf* b;
+    EC_TRY(new_buf(ct, len, &b));
+    if (len) {
+        EC_CUDA_TRY(cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming), "cudaEventCreate");
+        // the block may have been recycled from work still queued on the current stream: upload after it
+        EC_CUDA_TRY(cudaEventRecord(b->ready, cur_stream()), "cudaEventRecord");
+        EC_CUDA_TRY(cudaStreamWaitEvent(g_ctx.upload, b->ready, 0), "cudaStreamWaitEvent");
+        if (cudaError_t e = cudaMemcpyAsync(b->dptr, host, len * kSize[ct], cudaMemcpyHostToDevice, g_ctx.upload)) {
+            ec_buf_free(b);
+            return cuda_fail(e, "cudaMemcpyAsync(H2D)");
+        }
+        EC_CUDA_TRY(cudaEventRecord(b->ready, g_ctx.upload), "cudaEventRecord");
+    }
+    *out = b;
+    return EC_OK;
+}
+ec_status ec_buf_wait(const ec_buf* b) {
+    if (b->ready) EC_CUDA_TRY(cudaEventSynchronize(b->ready), "cudaEventSynchronize");
+    return EC_OK;
+}
 ec_status ec_buf_with_defaults(size_t len, uint8_t ct, ec_buf** out) {
     EC_TRY(ensure());
     if (!ct_ok(ct)) return invalid("cell type");
@@ -650,7 +681,7 @@ ec_status ec_buf_clone(const ec_buf* b, ec_buf** out) {
     ec_buf* c;
     EC_TRY(new_buf(b->ct, b->len, &c));
     if (b->len) {
-        if (cudaError_t e = launch_copy(launch_ctx(), (int)kSize[b->ct], b->dptr, c->dptr, b->len)) { ec_buf_free(c); return cuda_fail(e, "clone"); }
+        if (cudaError_t e = launch_copy(launch_ctx(), (int)kSize[b->ct], rd(b), c->dptr, b->len)) { ec_buf_free(c); return cuda_fail(e, "clone"); }
         note_launch("clone");
     }
     *out = c;
@@ -658,6 +689,10 @@ ec_status ec_buf_clone(const ec_buf* b, ec_buf** out) {
 }
 void ec_buf_free(ec_buf* b) {
     if (!b) return;
+    if (b->ready) {
+        cudaEventSynchronize(b->ready);
+        cudaEventDestroy(b->ready);
+    }
     if (b->owned) dev_free(b->dptr);
     delete b;
 }
@@ -668,7 +703,7 @@ ec_status ec_buf_to_host(const ec_buf* b, void* host, size_t host_bytes) {
     EC_TRY(ensure());
     const size_t bytes = b->len * kSize[b->ct];
     if (host_bytes < bytes) return invalid("ec_buf_to_host: host buffer too small");
-    if (bytes) EC_CUDA_TRY(cudaMemcpyAsync(host, b->dptr, bytes, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
+    if (bytes) EC_CUDA_TRY(cudaMemcpyAsync(host, rd(b), bytes, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
     return sync_stream();
 }
 ec_status ec_buf_get(const ec_buf* b, size_t index, ec_value* out) {
@@ -677,7 +712,7 @@ ec_status ec_buf_get(const ec_buf* b, size_t index, ec_value* out) {
     uint64_t* pin;
     EC_TRY(pinned_words(&pin));
     pin[0] = 0;
-    EC_CUDA_TRY(cudaMemcpyAsync(pin, static_cast<const char*>(b->dptr) + index * kSize[b->ct], kSize[b->ct], cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
+    EC_CUDA_TRY(cudaMemcpyAsync(pin, static_cast<const char*>(rd(b)) + index * kSize[b->ct], kSize[b->ct], cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
     EC_TRY(sync_stream());
     *out = tagged<uint64_t>(b->ct, pin[0]);
     return EC_OK;
@@ -691,7 +726,7 @@ ec_status ec_buf_put(ec_buf* b, size_t index, const ec_value* value) {
     uint64_t* pin;
     EC_TRY(pinned_words(&pin));
     pin[1] = c.bits;
-    EC_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(b->dptr) + index * kSize[b->ct], &pin[1], kSize[b->ct], cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
+    EC_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(rd(b)) + index * kSize[b->ct], &pin[1], kSize[b->ct], cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
     return sync_stream();
 }
 ec_status ec_buf_extend_host(ec_buf* b, uint8_t ct, const void* host, size_t n) {
@@ -705,7 +740,7 @@ ec_status ec_buf_extend_host(ec_buf* b, uint8_t ct, const void* host, size_t n) 
     const size_t new_len = b->len + n, sz = kSize[b->ct];
     void* grown;
     EC_TRY(dev_alloc(&grown, new_len * sz));
-    if (b->len) EC_CUDA_TRY(cudaMemcpyAsync(grown, b->dptr, b->len * sz, cudaMemcpyDeviceToDevice, cur_stream()), "cudaMemcpyAsync(D2D)");
+    if (b->len) EC_CUDA_TRY(cudaMemcpyAsync(grown, rd(b), b->len * sz, cudaMemcpyDeviceToDevice, cur_stream()), "cudaMemcpyAsync(D2D)");
     char* dst = static_cast<char*>(grown) + b->len * sz;
     if (ct == b->ct) {
         EC_CUDA_TRY(cudaMemcpyAsync(dst, host, n * sz, cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
@@ -739,7 +774,7 @@ ec_status ec_buf_binary(int op, const ec_buf* l, const ec_buf* r, ec_buf** out) 
     if (n == 0) return empty_result(out);
     ec_buf* o;
     EC_TRY(new_buf(EC_FLOAT64, n, &o));
-    if (cudaError_t e = launch_binary(launch_ctx(), op, l->ct, l->dptr, r->ct, r->dptr, static_cast<double*>(o->dptr), n, nullptr, nullptr, nullptr)) {
+    if (cudaError_t e = launch_binary(launch_ctx(), op, l->ct, rd(l), r->ct, rd(r), static_cast<double*>(o->dptr), n, nullptr, nullptr, nullptr)) {
         ec_buf_free(o);
         return cuda_fail(e, "binary");
     }
@@ -755,7 +790,7 @@ ec_status ec_buf_scalar(int op, const ec_buf* l, const ec_value* r, ec_buf** out
     EC_TRY(new_buf(EC_FLOAT64, l->len, &o));
     // unify() is value-exact, so the rhs the reference feeds to the f64 op is `r as f64`
     const double s = value_as_f64(*r);
-    if (cudaError_t e = launch_scalar(launch_ctx(), op, l->ct, l->dptr, s, static_cast<double*>(o->dptr), l->len)) {
+    if (cudaError_t e = launch_scalar(launch_ctx(), op, l->ct, rd(l), s, static_cast<double*>(o->dptr), l->len)) {
         ec_buf_free(o);
         return cuda_fail(e, "scalar");
     }
@@ -769,7 +804,7 @@ ec_status ec_buf_neg(const ec_buf* b, ec_buf** out) {
     if (b->len == 0) return empty_result(out);
     ec_buf* o;
     EC_TRY(new_buf(kNegOut[b->ct], b->len, &o));
-    if (cudaError_t e = launch_neg(launch_ctx(), b->ct, b->dptr, o->dptr, b->len)) { ec_buf_free(o); return cuda_fail(e, "neg"); }
+    if (cudaError_t e = launch_neg(launch_ctx(), b->ct, rd(b), o->dptr, b->len)) { ec_buf_free(o); return cuda_fail(e, "neg"); }
     note_launch("neg");
     *out = o;
     return EC_OK;
@@ -782,7 +817,7 @@ ec_status ec_buf_convert(const ec_buf* b, uint8_t ct, ec_buf** out) {
     if (b->len == 0) return empty_result(out);               // collect() of nothing, src/buffer.rs:234
     ec_buf* o;
     EC_TRY(new_buf(ct, b->len, &o));
-    if (cudaError_t e = launch_convert(launch_ctx(), b->ct, b->dptr, ct, o->dptr, b->len)) { ec_buf_free(o); return cuda_fail(e, "convert"); }
+    if (cudaError_t e = launch_convert(launch_ctx(), b->ct, rd(b), ct, o->dptr, b->len)) { ec_buf_free(o); return cuda_fail(e, "convert"); }
     note_launch("convert");
     *out = o;
     return EC_OK;
@@ -813,7 +848,7 @@ ec_status ec_buf_cmp(const ec_buf* l, const ec_buf* r, int* ordering) {
     if (n) {
         ReduceScratch sc;
         EC_TRY(reduce_scratch(&sc));
-        EC_LAUNCH(launch_first_diff(launch_ctx(), (int)kSize[l->ct], l->dptr, r->dptr, n, sc), "first_diff");
+        EC_LAUNCH(launch_first_diff(launch_ctx(), (int)kSize[l->ct], rd(l), rd(r), n, sc), "first_diff");
         uint64_t* pin;
         EC_TRY(pinned_words(&pin));
         EC_CUDA_TRY(cudaMemcpyAsync(pin, sc.result, 16, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
@@ -838,7 +873,7 @@ ec_status ec_buf_normalized_difference(const ec_buf* a, const ec_buf* b, ec_buf*
     if (n == 0) return empty_result(out);
     ec_buf* o;
     EC_TRY(new_buf(EC_FLOAT64, n, &o));
-    if (cudaError_t e = launch_normdiff(launch_ctx(), a->ct, a->dptr, b->ct, b->dptr, static_cast<double*>(o->dptr), n)) { ec_buf_free(o); return cuda_fail(e, "normdiff"); }
+    if (cudaError_t e = launch_normdiff(launch_ctx(), a->ct, rd(a), b->ct, rd(b), static_cast<double*>(o->dptr), n)) { ec_buf_free(o); return cuda_fail(e, "normdiff"); }
     note_launch("normalized_difference");
     *out = o;
     return EC_OK;
@@ -850,7 +885,7 @@ ec_status ec_buf_binary_scalar(int op1, const ec_buf* l, const ec_buf* r, int op
     if (n == 0) return empty_result(out);
     ec_buf* o;
     EC_TRY(new_buf(EC_FLOAT64, n, &o));
-    if (cudaError_t e = launch_binary_scalar(launch_ctx(), op1, l->ct, l->dptr, r->ct, r->dptr, op2, value_as_f64(*s), static_cast<double*>(o->dptr), n)) { ec_buf_free(o); return cuda_fail(e, "binary_scalar"); }
+    if (cudaError_t e = launch_binary_scalar(launch_ctx(), op1, l->ct, rd(l), r->ct, rd(r), op2, value_as_f64(*s), static_cast<double*>(o->dptr), n)) { ec_buf_free(o); return cuda_fail(e, "binary_scalar"); }
     note_launch("binary_scalar");
     *out = o;
     return EC_OK;
@@ -1031,7 +1066,7 @@ ec_status ec_mask_from_nodata(const ec_buf* b, int kind, const ec_value* v, ec_m
     if (nd.ct != b->ct) return invalid("NoData<T>: T must be the buffer's cell type");
     ec_mask* m;
     EC_TRY(new_mask(b->len, &m));
-    if (b->len) EC_LAUNCH(launch_mask_build(launch_ctx(), (int)kSize[b->ct], b->dptr, b->len, nd.bits, false, m->words), "mask_from_nodata");
+    if (b->len) EC_LAUNCH(launch_mask_build(launch_ctx(), (int)kSize[b->ct], rd(b), b->len, nd.bits, false, m->words), "mask_from_nodata");
     *out = m;
     return EC_OK;
 }
@@ -1046,7 +1081,7 @@ ec_status ec_buf_fill_nodata(const ec_buf* b, const ec_mask* m, uint8_t dst_ct, 
     ec_buf* o;
     EC_TRY(new_buf(dst_ct, b->len, &o));
     if (b->len) {
-        if (cudaError_t e = launch_fill_nodata(launch_ctx(), b->ct, b->dptr, m->words, dst_ct, o->dptr, b->len, nd.bits)) { ec_buf_free(o); return cuda_fail(e, "fill_nodata"); }
+        if (cudaError_t e = launch_fill_nodata(launch_ctx(), b->ct, rd(b), m->words, dst_ct, o->dptr, b->len, nd.bits)) { ec_buf_free(o); return cuda_fail(e, "fill_nodata"); }
         note_launch("fill_nodata");
     }
     *out = o;
@@ -1064,7 +1099,7 @@ ec_status ec_masked_binary(int op, const ec_buf* lbuf, const ec_mask* lmask, con
     ec_buf* o;
     if (ec_status s = new_buf(EC_FLOAT64, n, &o)) { ec_mask_free(om); return s; }
     // The shorter operand's mask has no bits past n, so `&` leaves the last word's tail zero.
-    if (cudaError_t e = launch_binary(launch_ctx(), op, lbuf->ct, lbuf->dptr, rbuf->ct, rbuf->dptr, static_cast<double*>(o->dptr), n,
+    if (cudaError_t e = launch_binary(launch_ctx(), op, lbuf->ct, rd(lbuf), rbuf->ct, rd(rbuf), static_cast<double*>(o->dptr), n,
                                       lmask->words, rmask->words, om->words)) {
         ec_buf_free(o); ec_mask_free(om);
         return cuda_fail(e, "masked_binary");

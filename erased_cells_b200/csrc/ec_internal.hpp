@@ -14,6 +14,7 @@ struct ec_buf {
     size_t len;
     size_t capacity_bytes;
     void* dptr;
+    cudaEvent_t ready;  // set by ec_buf_from_host_async: readers on other streams wait on it
 };
 struct ec_mask {
     size_t len;

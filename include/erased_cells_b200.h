@@ -143,6 +143,11 @@ ec_status ec_value_to_u64(const ec_value* v, uint64_t* out, int* is_some);      
 /* ---- CellBuffer — src/buffer.rs ------------------------------------------------------------- */
 /* from_vec / From<Vec<T>> / From<&[T]> (:64-66, :252-276): one H2D copy of `len` cells */
 ec_status ec_buf_from_host(uint8_t ct, const void* host, size_t len, ec_buf** out);
+/* Same, without blocking: the H2D copy runs on the library's upload stream (full-duplex with D2H traffic of
+ * the compute stream); every later op on the buffer is ordered after it. `host` must stay valid until
+ * ec_buf_wait() returns — from_vec(Vec<T>) owns its Vec, so the Rust shim parks it in the buffer until then. */
+ec_status ec_buf_from_host_async(uint8_t ct, const void* host, size_t len, ec_buf** out);
+ec_status ec_buf_wait(const ec_buf* b);
 /* with_defaults (:68-77) */
 ec_status ec_buf_with_defaults(size_t len, uint8_t ct, ec_buf** out);
 /* fill (:79-88): type = the value's type */

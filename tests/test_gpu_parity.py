@@ -280,3 +280,20 @@ def test_synth_host_equals_device():
             h = synth.host(ct, 10007, 0xEC40, 123, kind, lo, hi, 50, 1)
             d = synth.device(ct, 10007, 0xEC40, 123, kind, lo, hi, 50, 1).to_vec()
             assert np.array_equal(bits(h), bits(d)), (ct, kind)
+
+
+def test_async_upload_orders_readers(orc):
+    """from_vec(wait=False): the H2D copy runs on the upload stream; every consumer is ordered after it."""
+    n = (1 << 24) + 5
+    hs = [synth.host(CellType.UInt16, n, 0x5150 + i) for i in range(4)]
+    bufs = [CellBuffer.from_vec(h, wait=False) for h in hs]          # four uploads in flight
+    outs = [b.convert(CellType.Float64) for b in bufs]                # consumers queued immediately
+    mms = [b.min_max() for b in bufs]
+    for h, o, mm in zip(hs, outs, mms):
+        assert np.array_equal(o.to_vec(), h.astype(np.float64))
+        omn, omx = orc.tight_min_max(h)
+        assert (mm[0].bits, mm[1].bits) == (omn.bits, omx.bits)
+    b = CellBuffer.from_vec(hs[0], wait=False)
+    del b                                                             # freeing with the copy in flight is safe
+    c = CellBuffer.from_vec(hs[1], wait=False).wait()
+    assert c == bufs[1]

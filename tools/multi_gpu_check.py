@@ -1,0 +1,71 @@
+"""Multi-GPU check (one rank per GPU, torchrun): row-strip sharded min_max / counts finished with one all-reduce,
+through both plumbing options — torch.distributed (NCCL) and the library's own ec_comm_* (dlopen'ed NCCL).
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import erased_cells_b200 as ec
+from erased_cells_b200 import CellBuffer, CellType, CellValue, MaskedCellBuffer, NoData, sharding, synth
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+L = ec.lib()
+ec._lib.check(L.ec_init(local))
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
+ec._lib.check(L.ec_set_stream(C.c_void_p(stream.cuda_stream)))
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+W = H = int(os.environ.get("EC_SIDE", 16384))
+off, ln = sharding.row_strip(W, H, world, rank)
+
+# --- the library's own communicator: unique id from rank 0, shipped with torch.distributed ----------
+idbuf = torch.zeros(128, dtype=torch.uint8)
+if rank == 0:
+    raw = (C.c_uint8 * 128)()
+    ec._lib.check(L.ec_comm_unique_id(raw))
+    idbuf = torch.tensor(list(raw), dtype=torch.uint8)
+idbuf = idbuf.cuda()
+dist.broadcast(idbuf, 0)
+raw = (C.c_uint8 * 128)(*idbuf.cpu().tolist())
+comm = C.c_void_p()
+ec._lib.check(L.ec_comm_init_rank(raw, world, rank, C.byref(comm)))
+
+ok = True
+for ct in (CellType.Float32, CellType.Int16, CellType.UInt8, CellType.Float64, CellType.UInt64):
+    kw = dict(kind=synth.FULL_BITS) if ct != CellType.Float32 else dict(kind=synth.REAL_RANGE, lo=-1e4, hi=1e4)
+    strip = synth.device(ct, ln, 0xEC40 + int(ct), index_offset=off, **kw)
+    # reference: the same raster reduced on ONE GPU (every rank builds the whole raster for the check)
+    whole = synth.device(ct, W * H, 0xEC40 + int(ct), index_offset=0, **kw)
+    wmn, wmx = whole.min_max()
+    a = sharding.min_max_sharded(strip)                        # torch.distributed NCCL all-reduce(MIN) of 2 x int64
+    mn, mx = ec._lib.Value(), ec._lib.Value()
+    ec._lib.check(L.ec_buf_min_max_sharded(comm, strip._h, None, C.byref(mn), C.byref(mx)))   # ec_comm NCCL
+    good = (a[0].bits, a[1].bits) == (wmn.bits, wmx.bits) == (mn.bits, mx.bits)
+    # masked + counts
+    nd = NoData.new(ct, whole.get(12345).value())
+    ms, mw = MaskedCellBuffer.from_buffer_with_nodata(strip, nd), MaskedCellBuffer.from_buffer_with_nodata(whole, nd)
+    b = sharding.min_max_sharded(strip, ms.mask())
+    wm = mw.min_max()
+    d, n = C.c_size_t(), C.c_size_t()
+    ec._lib.check(L.ec_mask_counts_sharded(comm, ms.mask()._h, C.byref(d), C.byref(n)))
+    good &= (b[0].bits, b[1].bits) == (wm[0].bits, wm[1].bits) and (d.value, n.value) == mw.counts() == sharding.counts_sharded(ms.mask())
+    if rank == 0:
+        print(f"{ct}: sharded x{world} == single GPU: {good}  min/max bits {a[0].bits:#x} {a[1].bits:#x} counts {(d.value, n.value)}")
+    ok &= good
+    del whole, strip, ms, mw
+
+t = torch.tensor([int(ok)], device="cuda")
+dist.all_reduce(t, op=dist.ReduceOp.MIN)
+L.ec_comm_destroy(comm)
+dist.destroy_process_group()
+if rank == 0:
+    print("MULTI_GPU_OK" if int(t.item()) else "MULTI_GPU_FAILED")
+sys.exit(0 if int(t.item()) else 1)
