@@ -733,30 +733,39 @@ ec_status ec_buf_extend_host(ec_buf* b, uint8_t ct, const void* host, size_t n) 
     EC_TRY(ensure());
     if (!ct_ok(ct)) return invalid("cell type");
     if (!b->owned) return invalid("cannot extend a wrapped buffer");
-    // `to_<p>().unwrap()` (src/buffer.rs:212) cannot fail for a legal widening; the remaining pairs
-    // would need a value-dependent range check and are refused like a narrowing convert.
-    if (!ct_fits(ct, b->ct)) return narrowing(ct, b->ct);
     if (n == 0) return EC_OK;
     const size_t new_len = b->len + n, sz = kSize[b->ct];
     void* grown;
     EC_TRY(dev_alloc(&grown, new_len * sz));
     if (b->len) EC_CUDA_TRY(cudaMemcpyAsync(grown, rd(b), b->len * sz, cudaMemcpyDeviceToDevice, cur_stream()), "cudaMemcpyAsync(D2D)");
     char* dst = static_cast<char*>(grown) + b->len * sz;
-    if (ct == b->ct) {
+    bool failed = false;
+    if (ct == b->ct && !(ct == EC_FLOAT32)) {  // same type: to_<p>() is the identity (f32 NaNs still pass through f64, below)
         EC_CUDA_TRY(cudaMemcpyAsync(dst, host, n * sz, cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
+        EC_TRY(sync_stream());
     } else {
-        void* stage;
+        // `c.into_cell_value().to_<p>().unwrap()` (src/buffer.rs:212): value-checked on the device
+        void *stage, *conv;
         EC_TRY(dev_alloc(&stage, n * kSize[ct]));
+        EC_TRY(dev_alloc(&conv, n * sz));  // the appended run starts at an arbitrary cell offset: cast into an aligned temp
+        ReduceScratch sc;
+        EC_TRY(reduce_scratch(&sc));
         EC_CUDA_TRY(cudaMemcpyAsync(stage, host, n * kSize[ct], cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
-        // the appended run starts at an arbitrary cell offset: cast into an aligned temp, then copy
-        void* conv;
-        EC_TRY(dev_alloc(&conv, n * sz));
-        EC_LAUNCH(launch_convert(launch_ctx(), ct, stage, b->ct, conv, n), "convert");
+        EC_CUDA_TRY(cudaMemsetAsync(sc.result, 0, 8, cur_stream()), "cudaMemsetAsync");
+        EC_LAUNCH(launch_checked_cast(launch_ctx(), ct, stage, b->ct, conv, n, reinterpret_cast<unsigned int*>(sc.result)), "checked_cast");
         EC_CUDA_TRY(cudaMemcpyAsync(dst, conv, n * sz, cudaMemcpyDeviceToDevice, cur_stream()), "cudaMemcpyAsync(D2D)");
+        uint64_t* pin;
+        EC_TRY(pinned_words(&pin));
+        EC_CUDA_TRY(cudaMemcpyAsync(pin, sc.result, 8, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
+        EC_TRY(sync_stream());  // `host` may be reused by the caller as soon as we return
+        failed = (pin[0] & 0xFFFFFFFFu) != 0;
         dev_free(stage);
         dev_free(conv);
     }
-    EC_TRY(sync_stream());  // `host` may be reused by the caller as soon as we return
+    if (failed) {  // a cell did not fit: the reference panics in `unwrap()`; the buffer is left untouched
+        dev_free(grown);
+        return narrowing(ct, b->ct);
+    }
     dev_free(b->dptr);
     b->dptr = grown;
     b->len = new_len;

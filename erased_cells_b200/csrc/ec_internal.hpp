@@ -55,6 +55,7 @@ cudaError_t launch_binary(const Launch& L, int op, int lct, const void* l, int r
 cudaError_t launch_scalar(const Launch& L, int op, int lct, const void* l, double s, double* out, size_t n);
 cudaError_t launch_neg(const Launch& L, int ct, const void* a, void* out, size_t n);
 cudaError_t launch_convert(const Launch& L, int sct, const void* a, int dct, void* out, size_t n);
+cudaError_t launch_checked_cast(const Launch& L, int sct, const void* a, int dct, void* out, size_t n, unsigned int* fail_flag);
 cudaError_t launch_copy(const Launch& L, int cell_bytes, const void* a, void* out, size_t n);
 cudaError_t launch_fill(const Launch& L, int ct, void* out, size_t n, uint64_t bits);
 cudaError_t launch_fill_nodata(const Launch& L, int sct, const void* a, const uint32_t* m, int dct, void* out,

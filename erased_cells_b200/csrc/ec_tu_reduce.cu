@@ -4,6 +4,8 @@
 #include "ec_mask.cuh"
 #include "ec_reduce.cuh"
 
+#include <limits>
+
 #ifndef EC_VB
 #define EC_VB 32
 #endif
@@ -13,13 +15,16 @@
 
 namespace ec {
 
-// Geometry picked from the tools/ubench sweep on B200 (profiles/r01_ubench_sweep.md): unmasked
-// min_max runs best with 512-thread CTAs, 4 x 32-byte loads in flight per thread and a grid of up to
-// 32 CTAs per SM (6.86-6.97 TB/s for f32/u8/i16/f64); the masked flavour with 2 loads in flight and
-// 8 CTAs per SM (6.77 TB/s).
-constexpr int kRedThreads = 512;
+// Geometry picked from the tools/ubench sweeps on B200 at 2^24, 2^26 and 2^28 cells (profiles/r01_ubench_*):
+// unmasked min_max: 256-thread CTAs, 4 x 32-byte loads in flight per thread, persistent grid of 4 CTAs per SM
+// (3.8 / 5.9 / 6.96 TB/s for f32 at the three sizes; larger persistent grids must match the resident capacity
+// exactly or lose a partial wave); masked: 512 threads, 2 loads in flight, 8 CTAs per SM (6.77 TB/s at 2^28).
+constexpr int kRedThreads = 256;
 constexpr int kRedUnroll = 4;
+constexpr int kRedCtasPerSm = 4;
+constexpr int kRedThreadsMasked = 512;
 constexpr int kRedUnrollMasked = 2;
+constexpr int kRedCtasPerSmMasked = 8;
 constexpr size_t kMaxReduceBlocks = 8192;  // size of ReduceScratch::partials (pairs), see ec_api.cu
 
 static int reduce_grid(size_t n, size_t tile, const Launch& Lc, int ctas_per_sm = 32) {
@@ -35,12 +40,12 @@ static cudaError_t min_max_t(const Launch& Lc, const void* a, const uint32_t* ma
     constexpr int V = EC_VB / sizeof(T);
     const okey_t<T> smin = to_key<T>(std::numeric_limits<T>::max()), smax = to_key<T>(std::numeric_limits<T>::lowest());
     if (mask) {
-        constexpr size_t TILE = size_t(kRedThreads) * V * kRedUnrollMasked;
-        min_max_kernel<T, true, EC_VB, kRedUnrollMasked, kRedThreads><<<reduce_grid(n, TILE, Lc, 8), kRedThreads, 0, Lc.stream>>>(
+        constexpr size_t TILE = size_t(kRedThreadsMasked) * V * kRedUnrollMasked;
+        min_max_kernel<T, true, EC_VB, kRedUnrollMasked, kRedThreadsMasked><<<reduce_grid(n, TILE, Lc, kRedCtasPerSmMasked), kRedThreadsMasked, 0, Lc.stream>>>(
             static_cast<const T*>(a), mask, n, smin, smax, s);
     } else {
         constexpr size_t TILE = size_t(kRedThreads) * V * kRedUnroll;
-        min_max_kernel<T, false, EC_VB, kRedUnroll, kRedThreads><<<reduce_grid(n, TILE, Lc, 32), kRedThreads, 0, Lc.stream>>>(
+        min_max_kernel<T, false, EC_VB, kRedUnroll, kRedThreads><<<reduce_grid(n, TILE, Lc, kRedCtasPerSm), kRedThreads, 0, Lc.stream>>>(
             static_cast<const T*>(a), nullptr, n, smin, smax, s);
     }
     return cudaGetLastError();
@@ -128,6 +133,81 @@ cudaError_t launch_mask_bitop(const Launch& Lc, int mop, const uint32_t* l, cons
 }
 cudaError_t launch_mask_fill(const Launch& Lc, uint32_t* out, size_t n, bool value) {
     mask_fill_kernel<kThreads><<<grid_for((n + 31) / 32, kThreads, Lc), kThreads, 0, Lc.stream>>>(out, n, value ? 0xFFFFFFFFu : 0u);
+    return cudaGetLastError();
+}
+
+// ---- Extend<C> (src/buffer.rs:205-221): value-checked cast `c.into_cell_value().to_<p>().unwrap()` ---------
+// num-traits chain: ints go through i64/u64 with range checks, floats truncate iff inside the target's range,
+// anything -> f32 goes through f64. A cell that does not fit raises the flag (the reference panics).
+template <class S, class D> __device__ __forceinline__ bool checked_conv(S v, D& o) {
+    if constexpr (std::is_same<D, double>::value) {
+        o = as_f64(v);
+        return true;
+    } else if constexpr (std::is_same<D, float>::value) {
+        const double x = as_f64(v);
+        if (x != x) {  // cvtsd2ss: sign, quiet bit, top payload bits
+            const uint64_t b = static_cast<uint64_t>(__double_as_longlong(x));
+            o = __uint_as_float(static_cast<uint32_t>((b >> 32) & 0x80000000u) | 0x7FC00000u | static_cast<uint32_t>((b >> 29) & 0x003FFFFFu));
+        } else {
+            o = __double2float_rn(x);
+        }
+        return true;
+    } else if constexpr (std::is_signed<D>::value) {
+        int64_t t;
+        if constexpr (is_fp<S>) {
+            const double x = static_cast<double>(v);
+            if (!(x >= -9223372036854775808.0 && x < 9223372036854775808.0)) return false;
+            t = __double2ll_rz(x);
+        } else if constexpr (std::is_same<S, uint64_t>::value) {
+            if (v > static_cast<uint64_t>(INT64_MAX)) return false;
+            t = static_cast<int64_t>(v);
+        } else {
+            t = static_cast<int64_t>(v);
+        }
+        constexpr int64_t hi = sizeof(D) == 8 ? INT64_MAX : (int64_t(1) << (8 * sizeof(D) - 1)) - 1, lo = -hi - 1;
+        if (t < lo || t > hi) return false;
+        o = static_cast<D>(t);
+        return true;
+    } else {
+        uint64_t t;
+        if constexpr (is_fp<S>) {
+            const double x = static_cast<double>(v);
+            if (!(x > -1.0 && x < 18446744073709551616.0)) return false;
+            t = __double2ull_rz(x);
+        } else if constexpr (std::is_signed<S>::value) {
+            if (v < 0) return false;
+            t = static_cast<uint64_t>(v);
+        } else {
+            t = static_cast<uint64_t>(v);
+        }
+        constexpr uint64_t hi = sizeof(D) == 8 ? UINT64_MAX : (uint64_t(1) << (8 * sizeof(D))) - 1;
+        if (t > hi) return false;
+        o = static_cast<D>(t);
+        return true;
+    }
+}
+template <class S>
+__global__ void __launch_bounds__(kThreads) checked_cast_kernel(const S* __restrict__ a, int dct, void* __restrict__ out, size_t n,
+                                                                unsigned int* __restrict__ fail) {
+    bool ok = true;
+    for (size_t i = blockIdx.x * size_t(kThreads) + threadIdx.x; i < n; i += size_t(gridDim.x) * kThreads) {
+        const S v = a[i];
+        switch (dct) {
+#define X(id, p) case id: ok &= checked_conv<S, p>(v, static_cast<p*>(out)[i]); break;
+            EC_WITH_CT(X)
+#undef X
+        }
+    }
+    if (!ok) atomicOr(fail, 1u);
+}
+cudaError_t launch_checked_cast(const Launch& Lc, int sct, const void* a, int dct, void* out, size_t n, unsigned int* fail) {
+    const int grid = reduce_grid(n, kThreads * 4, Lc);
+    switch (sct) {
+#define X(id, p) case id: checked_cast_kernel<p><<<grid, kThreads, 0, Lc.stream>>>(static_cast<const p*>(a), dct, out, n, fail); break;
+        EC_WITH_CT(X)
+#undef X
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 

@@ -484,6 +484,27 @@ inline Status faithful_convert(const CellBuffer& b, CellType cell_type, CellBuff
     *out = collect(tmp);
     return Ok;
 }
+// Extend<C> — src/buffer.rs:205-221: every appended cell goes through `c.into_cell_value().to_<p>().unwrap()`,
+// i.e. the VALUE-checked ToPrimitive chain (not the type-checked convert); `None` panics in the reference,
+// reported here as NarrowingError.
+inline Status faithful_checked_cast(const CellBuffer& src, CellType dst, CellBuffer* out) {
+    CellBuffer r = CellBuffer::with_defaults(src.len, dst);
+    const size_t sz = size_of(dst);
+    for (size_t i = 0; i < src.len; ++i) {
+        const CellValue v = src.get(i);
+        std::optional<CellValue> c;
+        switch (dst) {
+#define X(id, p) case id: c = to_prim<p>(v); break;
+            ECO_WITH_CT(X)
+#undef X
+        }
+        if (!c) return NarrowingError;
+        std::memcpy(r.bytes.data() + i * sz, &c->bits, sz);
+    }
+    *out = std::move(r);
+    return Ok;
+}
+
 // min_max — src/buffer.rs:169-173 (+ masked: src/masked/masked_buffer.rs:208-217); mask may be null
 inline std::pair<CellValue, CellValue> faithful_min_max(const CellBuffer& b, const uint8_t* mask) {
     CellValue amin = max_value(b.ct), amax = min_value(b.ct);

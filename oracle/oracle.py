@@ -102,6 +102,7 @@ def lib():
             "eco_buf_scalar": (None, [I, I, VP, SZ, PV, C.POINTER(I), C.POINTER(SZ), VP]),
             "eco_buf_neg": (None, [I, VP, SZ, C.POINTER(I), C.POINTER(SZ), VP]),
             "eco_buf_convert": (I, [I, VP, SZ, I, C.POINTER(I), C.POINTER(SZ), VP]),
+            "eco_checked_cast": (I, [I, VP, SZ, I, VP]),
             "eco_buf_min_max": (None, [I, VP, SZ, VP, PV, PV]),
             "eco_buf_cmp": (I, [I, VP, SZ, I, VP, SZ]),
             "eco_buf_fill": (None, [SZ, PV, VP]),
@@ -248,6 +249,15 @@ def convert(a, dst: int) -> np.ndarray:
     if lib().eco_buf_convert(ct_of(a), _p(a), len(a), dst, C.byref(ct), C.byref(ln), _p(raw)) != OK:
         raise NarrowingError(ct_of(a), dst)
     return _result(ct, ln, raw)
+
+
+def checked_cast(a, dst: int) -> np.ndarray:
+    """Extend<C> semantics (src/buffer.rs:205-221): value-checked `to_<p>()`; a failing cell is the reference's panic."""
+    a = _c(a)
+    o = np.empty(len(a), dtype=DTYPES[dst])
+    if lib().eco_checked_cast(ct_of(a), _p(a), len(a), dst, _p(o)) != OK:
+        raise NarrowingError(ct_of(a), dst)
+    return o
 
 
 def min_max(a, mask=None):

@@ -91,6 +91,12 @@ int eco_buf_convert(int ct, const void* p, size_t n, int dst, int* out_ct, size_
     if (s == Ok) emit(r, out_ct, out_len, o);
     return s;
 }
+int eco_checked_cast(int ct, const void* p, size_t n, int dst, void* o) {
+    CellBuffer r;
+    Status s = faithful_checked_cast(CellBuffer::from_raw(CellType(ct), p, n), CellType(dst), &r);
+    if (s == Ok && n) std::memcpy(o, r.bytes.data(), r.bytes.size());
+    return s;
+}
 void eco_buf_min_max(int ct, const void* p, size_t n, const uint8_t* mask_or_null, eco_value* mn, eco_value* mx) {
     const CellBuffer buf = CellBuffer::from_raw(CellType(ct), p, n);
     std::pair<CellValue, CellValue> r;

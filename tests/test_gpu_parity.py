@@ -297,3 +297,39 @@ def test_async_upload_orders_readers(orc):
     del b                                                             # freeing with the copy in flight is safe
     c = CellBuffer.from_vec(hs[1], wait=False).wait()
     assert c == bufs[1]
+
+
+def test_extend_value_checked(orc):
+    """Extend<C> (src/buffer.rs:205-221): `to_<p>().unwrap()` is VALUE-checked — in-range values of a wider type
+    are accepted, anything else is the reference's panic (NarrowingError here), and the buffer stays untouched."""
+    for dct in CT:
+        for sct in CT:
+            base = cells(dct, 40, 0xABC + int(dct))
+            # small values fit every target
+            more = np.arange(0, 100, 7).astype(sct.dtype)
+            b = CellBuffer.from_vec(base)
+            b.extend(more)
+            want = np.concatenate([base, orc.checked_cast(more, int(dct))])
+            assert b.cell_type() == dct and np.array_equal(bits(b.to_vec()), bits(want)), (sct, dct)
+            # full-range values: either every cell fits (then bit-exact) or the call is refused
+            wild = cells(sct, 64, 0xDEF + int(sct))
+            b = CellBuffer.from_vec(base)
+            try:
+                w = orc.checked_cast(wild, int(dct))
+            except orc.NarrowingError:
+                with pytest.raises(ec.NarrowingError):
+                    b.extend(wild)
+                assert b.len() == 40 and np.array_equal(bits(b.to_vec()), bits(base))
+            else:
+                b.extend(wild)
+                assert np.array_equal(bits(b.to_vec()), bits(np.concatenate([base, w]))), (sct, dct)
+    # src/buffer.rs:496-505: `buf.extend([1])` — an i32 literal into a u8 buffer
+    buf = CellBuffer.fill(3, CellValue(CellType.UInt8, 0))
+    buf.extend(np.array([1], dtype=np.int32))
+    assert buf.cell_type() == CellType.UInt8 and list(buf.to_vec()) == [0, 0, 0, 1]
+    # floats truncate toward zero when in range, NaN never fits an integer
+    b = CellBuffer.from_vec(np.zeros(1, np.uint8))
+    b.extend(np.array([1.9, 254.99, -0.5]))
+    assert list(b.to_vec()) == [0, 1, 254, 0]
+    with pytest.raises(ec.NarrowingError):
+        b.extend(np.array([np.nan]))

@@ -18,12 +18,21 @@ using namespace ec;
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
 static int g_sms = 148;
+static size_t g_arena_in = size_t(1) << 30, g_arena_out = size_t(2) << 30;  // bytes
+static unsigned g_it = 0;
+// rotate through the arena so that small inputs are not L2-resident between launches
+template <class T> static T* rot(T* base, size_t n, size_t arena_bytes) {
+    size_t slots = arena_bytes / (n * sizeof(T));
+    if (slots < 1) slots = 1;
+    if (slots > 64) slots = 64;
+    return base + (g_it % slots) * n;
+}
 static cudaEvent_t g_e0, g_e1;
 static void* g_flush = nullptr;
 static size_t g_flush_bytes = 0;
 static ReduceScratch g_sc;
 
-template <class Fn> static float time_ms(Fn&& launch, int iters = 8) {
+template <class Fn> static float time_ms(Fn&& launch, int iters = 16) {
     for (int i = 0; i < 3; ++i) launch();
     CK(cudaDeviceSynchronize());
     float best = 1e30f, sum = 0;
@@ -59,7 +68,7 @@ static void run_map1(const char* op, const typename F::A* a, typename F::O* o, s
     constexpr size_t TILE = size_t(THREADS) * V * UNROLL;
     for (int cm : kCaps) {
         const int grid = grid_of(n, TILE, cm * g_sms);
-        float ms = time_ms([&] { map1_kernel<F, VB, UNROLL, THREADS><<<grid, THREADS>>>(a, o, n, f); });
+        float ms = time_ms([&] { ++g_it; map1_kernel<F, VB, UNROLL, THREADS><<<grid, THREADS>>>(rot(a, n, g_arena_in), rot(o, n, g_arena_out), n, f); });
         report(op, VB, UNROLL, THREADS, cm, bpc * n, ms);
     }
 }
@@ -70,7 +79,7 @@ static void run_map2(const char* op, const typename F::A* a, const typename F::B
     constexpr size_t TILE = size_t(THREADS) * V * UNROLL;
     for (int cm : kCaps) {
         const int grid = grid_of(n, TILE, cm * g_sms);
-        float ms = time_ms([&] { map2_kernel<F, VB, UNROLL, THREADS><<<grid, THREADS>>>(a, b, o, n, f, lm, rm, om); });
+        float ms = time_ms([&] { ++g_it; map2_kernel<F, VB, UNROLL, THREADS><<<grid, THREADS>>>(rot(a, n, g_arena_in), rot(b, n, g_arena_in), rot(o, n, g_arena_out), n, f, lm, rm, om); });
         report(op, VB, UNROLL, THREADS, cm, bpc * n, ms);
     }
 }
@@ -81,7 +90,7 @@ static void run_minmax(const char* op, const T* a, const uint32_t* m, size_t n, 
     const okey_t<T> smin = to_key<T>(std::numeric_limits<T>::max()), smax = to_key<T>(std::numeric_limits<T>::lowest());
     for (int cm : {2, 4, 8, 16, 32}) {
         const int grid = grid_of(n, TILE, cm * g_sms);
-        float ms = time_ms([&] { min_max_kernel<T, MASKED, VB, UNROLL, THREADS><<<grid, THREADS>>>(a, m, n, smin, smax, g_sc); });
+        float ms = time_ms([&] { ++g_it; min_max_kernel<T, MASKED, VB, UNROLL, THREADS><<<grid, THREADS>>>(rot(a, n, g_arena_in), m, n, smin, smax, g_sc); });
         report(op, VB, UNROLL, THREADS, cm, bpc * n, ms);
     }
 }
@@ -92,7 +101,7 @@ static void run_maskbuild(const char* op, const U* a, size_t n, uint32_t* out, d
     constexpr size_t TILE = size_t(THREADS) * V * UNROLL;
     for (int cm : kCaps) {
         const int grid = grid_of(n, TILE, cm * g_sms);
-        float ms = time_ms([&] { mask_build_kernel<U, false, VB, UNROLL, THREADS><<<grid, THREADS>>>(a, n, U(0x8000), out); });
+        float ms = time_ms([&] { ++g_it; mask_build_kernel<U, false, VB, UNROLL, THREADS><<<grid, THREADS>>>(rot(a, n, g_arena_in), n, U(0x8000), out); });
         report(op, VB, UNROLL, THREADS, cm, bpc * n, ms);
     }
 }
@@ -142,17 +151,19 @@ int main(int argc, char** argv) {
     CK(cudaEventCreate(&g_e0));
     CK(cudaEventCreate(&g_e1));
     void *in0, *in1, *out;
-    CK(cudaMalloc(&in0, n * 4));
-    CK(cudaMalloc(&in1, n * 4));
-    CK(cudaMalloc(&out, n * 8));
+    const size_t n0 = size_t(1) << 28;
+    if (n > n0) { fprintf(stderr, "n too large\n"); return 1; }
+    CK(cudaMalloc(&in0, g_arena_in));
+    CK(cudaMalloc(&in1, g_arena_in));
+    CK(cudaMalloc(&out, g_arena_out));
     uint32_t *m0, *m1, *m2;
-    CK(cudaMalloc(&m0, n / 8 * 2 + 64));
-    CK(cudaMalloc(&m1, n / 8 * 2 + 64));
-    CK(cudaMalloc(&m2, n / 8 * 2 + 64));
-    CK(cudaMemset(in0, 0x3C, n * 4));   // finite, non-zero patterns for every type
-    CK(cudaMemset(in1, 0x41, n * 4));
-    CK(cudaMemset(m0, 0xA5, n / 8 * 2));
-    CK(cudaMemset(m1, 0xFF, n / 8 * 2));
+    CK(cudaMalloc(&m0, n0 / 8 * 2 + 64));
+    CK(cudaMalloc(&m1, n0 / 8 * 2 + 64));
+    CK(cudaMalloc(&m2, n0 / 8 * 2 + 64));
+    CK(cudaMemset(in0, 0x3C, g_arena_in));   // finite, non-zero patterns for every type
+    CK(cudaMemset(in1, 0x41, g_arena_in));
+    CK(cudaMemset(m0, 0xA5, n0 / 8 * 2));
+    CK(cudaMemset(m1, 0xFF, n0 / 8 * 2));
     void* scratch;
     CK(cudaMalloc(&scratch, (2 * 8192 + 8) * 8));
     CK(cudaMemset(scratch, 0, (2 * 8192 + 8) * 8));
@@ -170,7 +181,7 @@ int main(int argc, char** argv) {
 
     {   // reference point: the runtime's own device-to-device copy
         printf("best_ms,avg_ms,");
-        float ms = time_ms([&] { CK(cudaMemcpyAsync(out, in0, n * 4, cudaMemcpyDeviceToDevice)); });
+        float ms = time_ms([&] { ++g_it; CK(cudaMemcpyAsync(rot((char*)out, n * 4, g_arena_out), rot((char*)in0, n * 4, g_arena_in), n * 4, cudaMemcpyDeviceToDevice)); });
         printf("memcpy_d2d,GBps=%.1f\n", 2.0 * n * 4 / (ms * 1e-3) / 1e9);
     }
     sweep<32, 1, 256>(n, in0, in1, out, m0, m1, m2);
