@@ -12,6 +12,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """The product is a compiled library: build it in-tree if this checkout has not been built yet
+    (nvcc cross-compiles for sm_100a without a GPU; __graft_entry__.build() does the same)."""
+    from erased_cells_b200 import _lib
+
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+
+
 @pytest.fixture(scope="session")
 def orc():
     """The CPU oracle (test infrastructure): compiled on demand with g++."""
