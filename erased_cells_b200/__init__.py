@@ -7,7 +7,22 @@ used by the parity tests and the bench. Nothing here computes cells on the CPU.
 from ._lib import EcError, NarrowingError, NoDeviceError, ParseError, build, lib  # noqa: F401
 from .api import CellBuffer, CellType, CellValue, Mask, MaskedCellBuffer, NoData  # noqa: F401
 
+import contextlib as _contextlib
+
 ADD, SUB, MUL, DIV = 0, 1, 2, 3
 
+
+@_contextlib.contextmanager
+def lazy(on: bool = True):
+    """Defer buffer arithmetic inside the block so that op chains fuse into single passes over HBM
+    (`(a - b) / (a + b)`, `(a op b) op scalar`); results are bit-identical to eager evaluation."""
+    from ._lib import check, lib
+    prev = lib().ec_get_lazy()
+    check(lib().ec_set_lazy(int(on)))
+    try:
+        yield
+    finally:
+        check(lib().ec_set_lazy(prev))
+
 __all__ = ["CellBuffer", "CellType", "CellValue", "Mask", "MaskedCellBuffer", "NoData", "NarrowingError",
-           "NoDeviceError", "EcError", "ParseError", "build", "lib", "ADD", "SUB", "MUL", "DIV"]
+           "NoDeviceError", "EcError", "ParseError", "build", "lib", "lazy", "ADD", "SUB", "MUL", "DIV"]

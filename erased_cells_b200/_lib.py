@@ -78,6 +78,8 @@ def _signatures():
         "ec_synchronize": (S, []),
         "ec_trim": (S, []),
         "ec_cached_bytes": (SZ, []),
+        "ec_set_lazy": (S, [I]),
+        "ec_get_lazy": (I, []),
         "ec_kernel_launches": (U64, []),
         "ec_last_kernel": (C.c_char_p, []),
         "ec_event_create": (S, [PVP]),

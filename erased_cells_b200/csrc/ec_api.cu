@@ -157,6 +157,13 @@ static void dev_free(void* p) {
     g_cache.free_by_stream[cur_stream()].emplace(it->second, p);
     g_cache.cached_bytes += it->second;
 }
+struct DevBlock {
+    void* p;
+    explicit DevBlock(void* q) : p(q) {}
+    DevBlock(const DevBlock&) = delete;
+    DevBlock& operator=(const DevBlock&) = delete;
+    ~DevBlock() { dev_free(p); }
+};
 static ec_status sync_stream() {
     if (cudaError_t e = cudaStreamSynchronize(cur_stream())) return cuda_fail(e, "cudaStreamSynchronize");
     return EC_OK;
@@ -361,9 +368,9 @@ static bool nodata_sentinel(int kind, uint8_t ct, const ec_value* v, ec_value* o
 
 // ---- handles -----------------------------------------------------------------------------------------
 static ec_status new_buf(uint8_t ct, size_t len, ec_buf** out) {
-    ec_buf* b = new ec_buf{ct, true, len, 0, nullptr};
-    b->capacity_bytes = len * kSize[ct];
+    ec_buf* b = new ec_buf{ct, true, len, len * kSize[ct], nullptr, nullptr, nullptr, nullptr};
     if (ec_status s = dev_alloc(&b->dptr, b->capacity_bytes)) { delete b; return s; }
+    if (b->dptr) b->blk = std::make_shared<DevBlock>(b->dptr);
     *out = b;
     return EC_OK;
 }
@@ -411,8 +418,122 @@ cudaError_t launch_binary_scalar(const Launch& L, int op1, int lct, const void* 
     return kBinScalar[lct](L, op1, l, rct, r, op2, s, out, n);
 }
 
+
+// ---- lazy op chains ---------------------------------------------------------
+// With ec_set_lazy(1) the arithmetic operators return a buffer whose value is a pending Expr over
+// refcounted snapshots of its operands. The first access evaluates it and recognises two shapes that
+// would otherwise cost extra passes over HBM:
+//     (X - Y) / (X + Y)      -> one normalized-difference kernel  (48 -> 12 B/cell for u16 NDVI)
+//     (X op1 Y) op2 scalar   -> one binary-then-scalar kernel      (27 -> 11 B/cell for u8/u16*0.5)
+// Every op keeps its own IEEE rounding, so results are bit-identical to eager evaluation. Operands are
+// immutable snapshots: put/extend on a buffer that a pending Expr still references copy it first.
+static thread_local bool t_lazy = false;
+enum : int { EX_BIN = 0, EX_SCALAR = 1 };
+struct Operand {
+    uint8_t ct = 0;
+    size_t len = 0;
+    const void* ptr = nullptr;
+    std::shared_ptr<DevBlock> blk;
+    std::shared_ptr<Expr> expr;
+};
+struct Expr {
+    int kind, op;
+    double s;
+    Operand l, r;
+    size_t n;
+    bool done = false;
+    std::shared_ptr<DevBlock> out;
+    void* out_ptr = nullptr;
+};
+static bool lazy_capable(const ec_buf* b) { return b->expr || b->blk; }  // wrapped memory is not ours to keep alive
+static Operand snapshot(const ec_buf* b) {
+    if (b->ready) cudaStreamWaitEvent(cur_stream(), b->ready, 0);
+    Operand o;
+    o.ct = b->ct; o.len = b->len; o.ptr = b->dptr; o.blk = b->blk; o.expr = b->expr;
+    return o;
+}
+static bool same_operand(const Operand& a, const Operand& b) {
+    if (a.expr || b.expr) return a.expr == b.expr;
+    return a.ptr == b.ptr && a.ct == b.ct && a.len == b.len;
+}
+static ec_status eval(Expr& e);
+static ec_status eval_operand(Operand& o) {
+    if (!o.expr) return EC_OK;
+    if (ec_status s = eval(*o.expr)) return s;
+    o.ptr = o.expr->out_ptr; o.blk = o.expr->out; o.ct = EC_FLOAT64; o.len = o.expr->n;
+    o.expr.reset();
+    return EC_OK;
+}
+static ec_status eval(Expr& e) {
+    if (e.done) return EC_OK;
+    void* out = nullptr;
+    if (ec_status s = dev_alloc(&out, e.n * sizeof(double))) return s;
+    std::shared_ptr<DevBlock> blk = std::make_shared<DevBlock>(out);
+    cudaError_t err;
+    const char* family;
+    Expr* cl = e.l.expr && !e.l.expr->done ? e.l.expr.get() : nullptr;
+    Expr* cr = e.kind == EX_BIN && e.r.expr && !e.r.expr->done ? e.r.expr.get() : nullptr;
+    if (e.kind == EX_SCALAR && cl && cl->kind == EX_BIN) {
+        if (ec_status s = eval_operand(cl->l)) return s;
+        if (ec_status s = eval_operand(cl->r)) return s;
+        err = launch_binary_scalar(launch_ctx(), cl->op, cl->l.ct, cl->l.ptr, cl->r.ct, cl->r.ptr, e.op, e.s, static_cast<double*>(out), e.n);
+        family = "binary_scalar(lazy)";
+    } else if (e.kind == EX_BIN && e.op == EC_DIV && cl && cr && cl->kind == EX_BIN && cr->kind == EX_BIN && cl->op == EC_SUB &&
+               cr->op == EC_ADD && same_operand(cl->l, cr->l) && same_operand(cl->r, cr->r)) {
+        if (ec_status s = eval_operand(cl->l)) return s;
+        if (ec_status s = eval_operand(cl->r)) return s;
+        err = launch_normdiff(launch_ctx(), cl->l.ct, cl->l.ptr, cl->r.ct, cl->r.ptr, static_cast<double*>(out), e.n);
+        family = "normalized_difference(lazy)";
+    } else {
+        if (ec_status s = eval_operand(e.l)) return s;
+        if (e.kind == EX_BIN) {
+            if (ec_status s = eval_operand(e.r)) return s;
+            err = launch_binary(launch_ctx(), e.op, e.l.ct, e.l.ptr, e.r.ct, e.r.ptr, static_cast<double*>(out), e.n, nullptr, nullptr, nullptr);
+            family = "binary";
+        } else {
+            err = launch_scalar(launch_ctx(), e.op, e.l.ct, e.l.ptr, e.s, static_cast<double*>(out), e.n);
+            family = "scalar";
+        }
+    }
+    if (err) return cuda_fail(err, family);
+    note_launch(family);
+    e.out = std::move(blk);
+    e.out_ptr = out;
+    e.done = true;
+    e.l = Operand();  // let the inputs go as early as possible
+    e.r = Operand();
+    return EC_OK;
+}
+// make a (possibly pending) buffer usable: after this b->dptr is valid
+static ec_status resolve(const ec_buf* b) {
+    if (!b->expr) return EC_OK;
+    ec_buf* m = const_cast<ec_buf*>(b);
+    if (ec_status s = eval(*m->expr)) return s;
+    m->dptr = m->expr->out_ptr;
+    m->blk = m->expr->out;
+    m->expr.reset();
+    return EC_OK;
+}
+static ec_buf* pending_buf(std::shared_ptr<Expr> e) {
+    ec_buf* b = new ec_buf{EC_FLOAT64, true, e->n, e->n * sizeof(double), nullptr, nullptr, nullptr, nullptr};
+    b->expr = std::move(e);
+    return b;
+}
+// in-place mutation of a block that pending Exprs still reference: copy first (operands are snapshots)
+static ec_status ensure_unique(ec_buf* b) {
+    if (!b->blk || b->blk.use_count() == 1) return EC_OK;
+    void* p = nullptr;
+    if (ec_status s = dev_alloc(&p, b->capacity_bytes)) return s;
+    if (cudaError_t e = launch_copy(launch_ctx(), (int)kSize[b->ct], b->dptr, p, b->len)) { dev_free(p); return cuda_fail(e, "clone"); }
+    note_launch("clone");
+    b->blk = std::make_shared<DevBlock>(p);
+    b->dptr = p;
+    return EC_OK;
+}
+
 // reduce a buffer to {min_key, max_key} (device, in scratch.result)
 static ec_status run_min_max(const ec_buf* b, const ec_mask* m, ReduceScratch* sc) {
+    EC_TRY(resolve(b));
     EC_TRY(reduce_scratch(sc));
     EC_LAUNCH(launch_min_max(launch_ctx(), b->ct, rd(b), m ? m->words : nullptr, b->len, *sc), "min_max");
     return EC_OK;
@@ -488,6 +609,11 @@ size_t ec_cached_bytes(void) {
     std::lock_guard<std::mutex> lk(g_cache.mu);
     return g_cache.cached_bytes;
 }
+ec_status ec_set_lazy(int on) {
+    t_lazy = on != 0;
+    return EC_OK;
+}
+int ec_get_lazy(void) { return t_lazy ? 1 : 0; }
 uint64_t ec_kernel_launches(void) { return g_launches.load(); }
 const char* ec_last_kernel(void) { return t_last_kernel; }
 ec_status ec_event_create(ec_event** out) {
@@ -648,6 +774,7 @@ ec_status ec_buf_from_host_async(uint8_t ct, const void* host, size_t len, ec_bu
     return EC_OK;
 }
 ec_status ec_buf_wait(const ec_buf* b) {
+    EC_TRY(resolve(b));
     if (b->ready) EC_CUDA_TRY(cudaEventSynchronize(b->ready), "cudaEventSynchronize");
     return EC_OK;
 }
@@ -673,11 +800,12 @@ ec_status ec_buf_wrap_device(uint8_t ct, void* device_ptr, size_t len, ec_buf** 
     EC_TRY(ensure());
     if (!ct_ok(ct)) return invalid("cell type");
     if (reinterpret_cast<uintptr_t>(device_ptr) % 32 != 0) return invalid("device pointer must be 32-byte aligned (row strips start on 128-cell boundaries)");
-    *out = new ec_buf{ct, false, len, len * kSize[ct], device_ptr};
+    *out = new ec_buf{ct, false, len, len * kSize[ct], device_ptr, nullptr, nullptr, nullptr};
     return EC_OK;
 }
 ec_status ec_buf_clone(const ec_buf* b, ec_buf** out) {
     EC_TRY(ensure());
+    EC_TRY(resolve(b));
     ec_buf* c;
     EC_TRY(new_buf(b->ct, b->len, &c));
     if (b->len) {
@@ -693,14 +821,14 @@ void ec_buf_free(ec_buf* b) {
         cudaEventSynchronize(b->ready);
         cudaEventDestroy(b->ready);
     }
-    if (b->owned) dev_free(b->dptr);
-    delete b;
+    delete b;  // the block goes back to the allocator when its last user (this handle or a pending Expr) lets go
 }
 size_t ec_buf_len(const ec_buf* b) { return b->len; }
 uint8_t ec_buf_ctype(const ec_buf* b) { return b->ct; }
-void* ec_buf_device_ptr(const ec_buf* b) { return b->dptr; }
+void* ec_buf_device_ptr(const ec_buf* b) { return resolve(b) == EC_OK ? b->dptr : nullptr; }
 ec_status ec_buf_to_host(const ec_buf* b, void* host, size_t host_bytes) {
     EC_TRY(ensure());
+    EC_TRY(resolve(b));
     const size_t bytes = b->len * kSize[b->ct];
     if (host_bytes < bytes) return invalid("ec_buf_to_host: host buffer too small");
     if (bytes) EC_CUDA_TRY(cudaMemcpyAsync(host, rd(b), bytes, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
@@ -708,6 +836,7 @@ ec_status ec_buf_to_host(const ec_buf* b, void* host, size_t host_bytes) {
 }
 ec_status ec_buf_get(const ec_buf* b, size_t index, ec_value* out) {
     EC_TRY(ensure());
+    EC_TRY(resolve(b));
     if (index >= b->len) { set_error("index out of bounds: the len is %zu but the index is %zu", b->len, index); return EC_OOB; }
     uint64_t* pin;
     EC_TRY(pinned_words(&pin));
@@ -723,6 +852,8 @@ ec_status ec_buf_put(ec_buf* b, size_t index, const ec_value* value) {
     if (!ct_fits(value->ct, b->ct)) return narrowing(value->ct, b->ct);  // convert()? happens before the index (src/buffer.rs:137)
     if (index >= b->len) { set_error("index out of bounds: the len is %zu but the index is %zu", b->len, index); return EC_OOB; }
     const ec_value c = value_widen(*value, b->ct);
+    EC_TRY(resolve(b));
+    EC_TRY(ensure_unique(b));
     uint64_t* pin;
     EC_TRY(pinned_words(&pin));
     pin[1] = c.bits;
@@ -734,6 +865,7 @@ ec_status ec_buf_extend_host(ec_buf* b, uint8_t ct, const void* host, size_t n) 
     if (!ct_ok(ct)) return invalid("cell type");
     if (!b->owned) return invalid("cannot extend a wrapped buffer");
     if (n == 0) return EC_OK;
+    EC_TRY(resolve(b));
     const size_t new_len = b->len + n, sz = kSize[b->ct];
     void* grown;
     EC_TRY(dev_alloc(&grown, new_len * sz));
@@ -766,7 +898,7 @@ ec_status ec_buf_extend_host(ec_buf* b, uint8_t ct, const void* host, size_t n) 
         dev_free(grown);
         return narrowing(ct, b->ct);
     }
-    dev_free(b->dptr);
+    b->blk = std::make_shared<DevBlock>(grown);  // the old block returns to the allocator once no pending Expr needs it
     b->dptr = grown;
     b->len = new_len;
     b->capacity_bytes = new_len * sz;
@@ -781,6 +913,14 @@ ec_status ec_buf_binary(int op, const ec_buf* l, const ec_buf* r, ec_buf** out) 
     if (op < 0 || op > 3) return invalid("op");
     const size_t n = std::min(l->len, r->len);  // zip (src/buffer.rs:327)
     if (n == 0) return empty_result(out);
+    if (t_lazy && lazy_capable(l) && lazy_capable(r)) {
+        auto e = std::make_shared<Expr>();
+        e->kind = EX_BIN; e->op = op; e->s = 0; e->l = snapshot(l); e->r = snapshot(r); e->n = n;
+        *out = pending_buf(std::move(e));
+        return EC_OK;
+    }
+    EC_TRY(resolve(l));
+    EC_TRY(resolve(r));
     ec_buf* o;
     EC_TRY(new_buf(EC_FLOAT64, n, &o));
     if (cudaError_t e = launch_binary(launch_ctx(), op, l->ct, rd(l), r->ct, rd(r), static_cast<double*>(o->dptr), n, nullptr, nullptr, nullptr)) {
@@ -795,10 +935,17 @@ ec_status ec_buf_scalar(int op, const ec_buf* l, const ec_value* r, ec_buf** out
     EC_TRY(ensure());
     if (op < 0 || op > 3 || !ct_ok(r->ct)) return invalid("op / cell type");
     if (l->len == 0) return empty_result(out);
-    ec_buf* o;
-    EC_TRY(new_buf(EC_FLOAT64, l->len, &o));
     // unify() is value-exact, so the rhs the reference feeds to the f64 op is `r as f64`
     const double s = value_as_f64(*r);
+    if (t_lazy && lazy_capable(l)) {
+        auto e = std::make_shared<Expr>();
+        e->kind = EX_SCALAR; e->op = op; e->s = s; e->l = snapshot(l); e->n = l->len;
+        *out = pending_buf(std::move(e));
+        return EC_OK;
+    }
+    EC_TRY(resolve(l));
+    ec_buf* o;
+    EC_TRY(new_buf(EC_FLOAT64, l->len, &o));
     if (cudaError_t e = launch_scalar(launch_ctx(), op, l->ct, rd(l), s, static_cast<double*>(o->dptr), l->len)) {
         ec_buf_free(o);
         return cuda_fail(e, "scalar");
@@ -811,6 +958,7 @@ static const uint8_t kNegOut[10] = {EC_INT16, EC_INT32, EC_FLOAT64, EC_FLOAT64, 
 ec_status ec_buf_neg(const ec_buf* b, ec_buf** out) {
     EC_TRY(ensure());
     if (b->len == 0) return empty_result(out);
+    EC_TRY(resolve(b));
     ec_buf* o;
     EC_TRY(new_buf(kNegOut[b->ct], b->len, &o));
     if (cudaError_t e = launch_neg(launch_ctx(), b->ct, rd(b), o->dptr, b->len)) { ec_buf_free(o); return cuda_fail(e, "neg"); }
@@ -824,6 +972,7 @@ ec_status ec_buf_convert(const ec_buf* b, uint8_t ct, ec_buf** out) {
     if (ct == b->ct) return ec_buf_clone(b, out);            // src/buffer.rs:151-153
     if (!ct_fits(b->ct, ct)) return narrowing(b->ct, ct);    // src/buffer.rs:155-159, before any launch
     if (b->len == 0) return empty_result(out);               // collect() of nothing, src/buffer.rs:234
+    EC_TRY(resolve(b));
     ec_buf* o;
     EC_TRY(new_buf(ct, b->len, &o));
     if (cudaError_t e = launch_convert(launch_ctx(), b->ct, rd(b), ct, o->dptr, b->len)) { ec_buf_free(o); return cuda_fail(e, "convert"); }
@@ -855,6 +1004,8 @@ ec_status ec_buf_cmp(const ec_buf* l, const ec_buf* r, int* ordering) {
     if (l->ct != r->ct) { *ordering = l->ct < r->ct ? -1 : 1; return EC_OK; }  // src/buffer.rs:395-398
     const size_t n = std::min(l->len, r->len);
     if (n) {
+        EC_TRY(resolve(l));
+        EC_TRY(resolve(r));
         ReduceScratch sc;
         EC_TRY(reduce_scratch(&sc));
         EC_LAUNCH(launch_first_diff(launch_ctx(), (int)kSize[l->ct], rd(l), rd(r), n, sc), "first_diff");
@@ -880,6 +1031,8 @@ ec_status ec_buf_normalized_difference(const ec_buf* a, const ec_buf* b, ec_buf*
     EC_TRY(ensure());
     const size_t n = std::min(a->len, b->len);
     if (n == 0) return empty_result(out);
+    EC_TRY(resolve(a));
+    EC_TRY(resolve(b));
     ec_buf* o;
     EC_TRY(new_buf(EC_FLOAT64, n, &o));
     if (cudaError_t e = launch_normdiff(launch_ctx(), a->ct, rd(a), b->ct, rd(b), static_cast<double*>(o->dptr), n)) { ec_buf_free(o); return cuda_fail(e, "normdiff"); }
@@ -892,6 +1045,8 @@ ec_status ec_buf_binary_scalar(int op1, const ec_buf* l, const ec_buf* r, int op
     if (op1 < 0 || op1 > 3 || op2 < 0 || op2 > 3 || !ct_ok(s->ct)) return invalid("op / cell type");
     const size_t n = std::min(l->len, r->len);
     if (n == 0) return empty_result(out);
+    EC_TRY(resolve(l));
+    EC_TRY(resolve(r));
     ec_buf* o;
     EC_TRY(new_buf(EC_FLOAT64, n, &o));
     if (cudaError_t e = launch_binary_scalar(launch_ctx(), op1, l->ct, rd(l), r->ct, rd(r), op2, value_as_f64(*s), static_cast<double*>(o->dptr), n)) { ec_buf_free(o); return cuda_fail(e, "binary_scalar"); }
@@ -1073,6 +1228,7 @@ ec_status ec_mask_from_nodata(const ec_buf* b, int kind, const ec_value* v, ec_m
     ec_value nd;
     if (!nodata_sentinel(kind, b->ct, v, &nd)) return ec_mask_fill(b->len, 1, out);  // NoData::None: all valid
     if (nd.ct != b->ct) return invalid("NoData<T>: T must be the buffer's cell type");
+    EC_TRY(resolve(b));
     ec_mask* m;
     EC_TRY(new_mask(b->len, &m));
     if (b->len) EC_LAUNCH(launch_mask_build(launch_ctx(), (int)kSize[b->ct], rd(b), b->len, nd.bits, false, m->words), "mask_from_nodata");
@@ -1087,6 +1243,7 @@ ec_status ec_buf_fill_nodata(const ec_buf* b, const ec_mask* m, uint8_t dst_ct, 
     if (!nodata_sentinel(kind, dst_ct, v, &nd)) return ec_buf_convert(b, dst_ct, out);
     if (nd.ct != dst_ct) return invalid("NoData<T>: T must be the target cell type");
     if (m->len != b->len) { set_error("Mask and buffer must have the same length."); return EC_LEN_MISMATCH; }
+    EC_TRY(resolve(b));
     ec_buf* o;
     EC_TRY(new_buf(dst_ct, b->len, &o));
     if (b->len) {
@@ -1105,6 +1262,15 @@ ec_status ec_masked_binary(int op, const ec_buf* lbuf, const ec_mask* lmask, con
     ec_mask* om;
     EC_TRY(new_mask(n, &om));
     if (n == 0) { *out_mask = om; return empty_result(out_buf); }
+    if (t_lazy && lazy_capable(lbuf) && lazy_capable(rbuf)) {  // data deferred (fusable), mask AND now
+        if (cudaError_t e = launch_mask_bitop(launch_ctx(), 1, lmask->words, rmask->words, n, om->words)) { ec_mask_free(om); return cuda_fail(e, "mask_bitop"); }
+        note_launch("mask_bitop");
+        if (ec_status s = ec_buf_binary(op, lbuf, rbuf, out_buf)) { ec_mask_free(om); return s; }
+        *out_mask = om;
+        return EC_OK;
+    }
+    EC_TRY(resolve(lbuf));
+    EC_TRY(resolve(rbuf));
     ec_buf* o;
     if (ec_status s = new_buf(EC_FLOAT64, n, &o)) { ec_mask_free(om); return s; }
     // The shorter operand's mask has no bits past n, so `&` leaves the last word's tail zero.

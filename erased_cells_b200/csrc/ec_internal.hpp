@@ -4,17 +4,25 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <memory>
 #include <string>
 
 #include "../../include/erased_cells_b200.h"
+
+namespace ec {
+struct DevBlock;  // refcounted device allocation (returns to the caching allocator when the last user lets go)
+struct Expr;      // a deferred op (lazy mode): evaluated, possibly fused with its children, on first use
+}  // namespace ec
 
 struct ec_buf {
     uint8_t ct;
     bool owned;
     size_t len;
     size_t capacity_bytes;
-    void* dptr;
+    void* dptr;         // null while `expr` is pending
     cudaEvent_t ready;  // set by ec_buf_from_host_async: readers on other streams wait on it
+    std::shared_ptr<ec::DevBlock> blk;
+    std::shared_ptr<ec::Expr> expr;
 };
 struct ec_mask {
     size_t len;

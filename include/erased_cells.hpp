@@ -140,6 +140,9 @@ inline CellValue one(CellType ct) { CellValue o; detail::check(ec_ctype_one(uint
 inline CellValue min_value(CellType ct) { CellValue o; detail::check(ec_ctype_min_value(uint8_t(ct), &o.v)); return o; }
 inline CellValue max_value(CellType ct) { CellValue o; detail::check(ec_ctype_max_value(uint8_t(ct), &o.v)); return o; }
 
+// Defer buffer arithmetic on this thread so op chains fuse into single passes over HBM (bit-identical results).
+inline void set_lazy(bool on) { detail::check(ec_set_lazy(on ? 1 : 0)); }
+
 // ---- CellBuffer — src/buffer.rs; BufferOps — src/lib.rs:104-163 -----------------------------------------------
 class Mask;
 class CellBuffer {

@@ -180,7 +180,13 @@ ec_status ec_buf_min_max(const ec_buf* b, const ec_mask* mask_or_null, ec_value*
 /* Ord/Eq for CellBuffer (:373-436): cell type, then lexicographic total order, then length */
 ec_status ec_buf_cmp(const ec_buf* l, const ec_buf* r, int* ordering);
 
-/* ---- fused op chains behind the same operators ------------------------- */
+/* ---- fused op chains behind the same operators -------------------------
+ * ec_set_lazy(1) (per thread, default 0): ec_buf_binary / ec_buf_scalar / ec_masked_binary return at once with a
+ * pending result over refcounted snapshots of their operands; the first access evaluates it, fusing
+ * `(X - Y) / (X + Y)` and `(X op1 Y) op2 scalar` into one pass over HBM. Results are bit-identical to eager
+ * evaluation; later put/extend on an operand do not affect a pending result (copy on write). */
+ec_status ec_set_lazy(int on);
+int ec_get_lazy(void);
 /* `(&a - &b) / (&a + &b)` with the three roundings of the unfused chain; 1 pass over HBM */
 ec_status ec_buf_normalized_difference(const ec_buf* a, const ec_buf* b, ec_buf** out);
 /* `(l op1 r) op2 s`, e.g. README `buf1 / buf2 * 0.5` */

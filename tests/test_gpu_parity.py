@@ -333,3 +333,52 @@ def test_extend_value_checked(orc):
     assert list(b.to_vec()) == [0, 1, 254, 0]
     with pytest.raises(ec.NarrowingError):
         b.extend(np.array([np.nan]))
+
+
+def test_lazy_chains_fuse_and_match_eager(orc):
+    """ec.lazy(): operators defer, the first access evaluates — (a-b)/(a+b) and (a op b) op s as ONE kernel each,
+    bit-identical to eager evaluation; operands are snapshots (drop / mutate them freely afterwards)."""
+    L = ec.lib()
+    for (lct, rct) in [(CellType.UInt16, CellType.UInt16), (CellType.UInt8, CellType.UInt16), (CellType.Float32, CellType.Int64), (CellType.Float64, CellType.Float64)]:
+        n = 3 * 32768 + 11
+        l, r = cells(lct, n, 0x1A2), cells(rct, n, 0x1A3)
+        if lct == rct:
+            r[5::7] = l[5::7]
+        a, b = CellBuffer.from_vec(l), CellBuffer.from_vec(r)
+        eager_ndvi = (a - b) / (a + b)
+        eager_chain = a / b * 0.5
+        with ec.lazy():
+            k0 = L.ec_kernel_launches()
+            ndvi = (a - b) / (a + b)
+            chain = a / b * 0.5
+            deep = ((a + b) * 2.0 - a) / b                      # no special shape: evaluated op by op
+            assert L.ec_kernel_launches() == k0                 # nothing has run yet
+            assert ndvi.cell_type() == CellType.Float64 and ndvi.len() == n
+            got = ndvi.to_vec()
+            assert L.ec_kernel_launches() == k0 + 1 and L.ec_last_kernel() == b"normalized_difference(lazy)"
+            assert np.array_equal(bits(got), bits(eager_ndvi.to_vec()))
+            got = chain.to_vec()
+            assert L.ec_kernel_launches() == k0 + 2 and L.ec_last_kernel() == b"binary_scalar(lazy)"
+            assert np.array_equal(bits(got), bits(eager_chain.to_vec()))
+            want = orc.tight_binary(orc.DIV, orc.tight_binary(orc.SUB, orc.tight_scalar(orc.MUL, orc.tight_binary(orc.ADD, l, r), orc.value(orc.Float64, 2.0)), l), r)
+            assert np.array_equal(bits(deep.to_vec()), bits(want))
+            # operands are snapshots: dropping or mutating them after the fact does not change a pending result
+            x, y = CellBuffer.from_vec(l), CellBuffer.from_vec(r)
+            pend = (x - y) / (x + y)
+            x.put(0, x.get(1))
+            y.extend(r[:3])
+            del y
+            assert pend == eager_ndvi and x.get(0) == x.get(1)
+            # a shared sub-expression used twice is evaluated once and stays correct
+            num = a - b
+            both = (num / (a + b), num * 3.0)
+            assert both[0] == eager_ndvi and np.array_equal(bits(both[1].to_vec()), bits(orc.tight_scalar(orc.MUL, orc.tight_binary(orc.SUB, l, r), orc.value(orc.Float64, 3.0))))
+            assert np.array_equal(bits(num.to_vec()), bits(orc.tight_binary(orc.SUB, l, r)))
+            # reductions and masked ops see through pending values
+            mm = ((a - b) / (a + b)).min_max()
+            assert (mm[0].bits, mm[1].bits) == tuple(v.bits for v in eager_ndvi.min_max())
+            ma, mb = MaskedCellBuffer.from_vec(l), MaskedCellBuffer.from_vec(r)
+            mr = (ma - mb) / (ma + mb)
+            assert mr.buffer() == eager_ndvi and mr.counts() == (n, 0)
+            assert (CellBuffer.from_vec(l[:0]) + a).cell_type() == CellType.UInt8   # empty stays the reference's UInt8([])
+        assert not L.ec_get_lazy()
