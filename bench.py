@@ -189,6 +189,24 @@ def run_reference(args):
     }))
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, so the pinned host buffers of the e2e leg are
+    allocated on the GPU's NUMA node (torchrun does not bind ranks; cross-socket DMA halves PCIe throughput)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 # =================================================================================================
 # this repo's arm
 # =================================================================================================
@@ -213,8 +231,9 @@ def run_ours(args):
     assert stream.cuda_stream != 0
     ec._lib.check(L.ec_set_stream(C.c_void_p(stream.cuda_stream)))
     assert L.ec_get_stream() == stream.cuda_stream
+    bind_to_gpu_numa_node(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("EC_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version/debug lines go to stderr: stdout is the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -440,8 +459,15 @@ def other_configs(ec, L, torch, dist, rank, world, barrier, max_over_ranks, peak
     def c1_fused():
         a, b = sets[it[0] % 8]; it[0] += 1
         return a.binary_scalar(ec.DIV, b, ec.MUL, 0.5)
+    def c1_lazy():  # the README expression itself, deferred: `a / b * 0.5` runs as one fused kernel on first access
+        a, b = sets[it[0] % 8]; it[0] += 1
+        with ec.lazy():
+            r = a / b * 0.5
+            r.device_ptr()
+        return r
     res["c1_readme_4096"] = {"div_u8_u16": entry(timed(c1_div, 16), 11 * n1, n1), "div_then_mul_unfused": entry(timed(c1_unfused, 16), 27 * n1, n1),
-                             "div_mul_fused": entry(timed(c1_fused, 16), 11 * n1, n1), "scaling": "weak (same buffers on every rank)"}
+                             "div_mul_fused": entry(timed(c1_fused, 16), 11 * n1, n1), "div_mul_lazy_operators": entry(timed(c1_lazy, 16), 11 * n1, n1),
+                             "scaling": "weak (same buffers on every rank)"}
     del sets
 
     # config 3: masked i16 16384^2 with NoData: (a - b) * s, min_max, counts
@@ -479,7 +505,15 @@ def other_configs(ec, L, torch, dist, rank, world, barrier, max_over_ranks, peak
         return mn.bits, mx.bits
     ms4 = timed(c4, 10)
     res["c4_f32_32768_min_max_sharded"] = entry(ms4, 4.0 * n4, n4, scaling="strong", shards=world, result_bits=[hex(x) for x in c4()],
-                                                note="shard kernel + all-reduce(MIN, 2 x int64) + D2H of the result, host-visible")
+                                                note="shard kernel + torch.distributed all-reduce(MIN, 2 x int64) + D2H of the result, host-visible")
+    if world > 1:  # the same through the library's communicator: reduction + NVLink peer exchange + final fold in ONE kernel per GPU
+        from erased_cells_b200 import sharding
+        comm = sharding.Comm.create()
+        got = comm.min_max(strip)
+        res["c4_f32_32768_min_max_sharded_fused"] = entry(timed(lambda: comm.min_max(strip), 10), 4.0 * n4, n4, scaling="strong", shards=world,
+                                                          peer_exchange=comm.peer_exchange, result_bits=[hex(got[0].bits), hex(got[1].bits)],
+                                                          note="ec_buf_min_max_sharded: one kernel per GPU when peer_exchange is true, else kernel + NCCL")
+        comm.close()
     del strip
 
     # config 5: NDVI (nir - red) / (nir + red), u16 32768^2 -> f64, one tile per GPU (weak)
@@ -490,6 +524,12 @@ def other_configs(ec, L, torch, dist, rank, world, barrier, max_over_ranks, peak
         "unfused_3_ops": entry(timed(lambda: (nir - red) / (nir + red), 3, 1), 48.0 * n5, n5),
         "fused_1_pass": entry(timed(lambda: nir.normalized_difference(red), 3, 1), 12.0 * n5, n5),
         "scaling": "weak (one tile per GPU)"}
+    def c5_lazy():  # `(&nir - &red) / (&nir + &red)` through the operators, deferred -> one fused pass
+        with ec.lazy():
+            r = (nir - red) / (nir + red)
+            r.device_ptr()
+        return r
+    res["c5_ndvi_u16_32768_per_gpu_tile"]["lazy_operators_1_pass"] = entry(timed(c5_lazy, 3, 1), 12.0 * n5, n5)
     nd5 = nir.normalized_difference(red)
     res["c5_ndvi_u16_32768_per_gpu_tile"]["min_max_f64"] = entry(timed(lambda: nd5.min_max(), 3, 1), 8.0 * n5, n5)
     return res

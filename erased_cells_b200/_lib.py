@@ -158,6 +158,7 @@ def _signatures():
         "ec_comm_unique_id": (S, [VP]),
         "ec_comm_init_rank": (S, [VP, I, I, PVP]),
         "ec_comm_destroy": (None, [VP]),
+        "ec_comm_peer_exchange": (I, [VP]),
         "ec_comm_allreduce_min_i64": (S, [VP, VP, SZ]),
         "ec_comm_allreduce_sum_u64": (S, [VP, VP, SZ]),
         "ec_buf_min_max_sharded": (S, [VP, VP, VP, PV, PV]),

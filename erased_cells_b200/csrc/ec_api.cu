@@ -76,7 +76,8 @@ static thread_local bool t_device_bound = false;
 
 struct ThreadScratch {
     std::vector<std::pair<cudaStream_t, ReduceScratch>> per_stream;
-    uint64_t* pinned = nullptr;  // 8 words of pinned host staging for scalar results
+    uint64_t* pinned = nullptr;      // 16 words of pinned, device-mapped host memory for scalar results
+    uint64_t* pinned_dev = nullptr;  // its device alias: reduction kernels write results [8..11] straight into it
 };
 static thread_local ThreadScratch t_scratch;
 constexpr size_t kMaxReduceBlocks = 8192;
@@ -170,7 +171,9 @@ static ec_status sync_stream() {
 }
 static ec_status pinned_words(uint64_t** out) {
     if (!t_scratch.pinned) {
-        if (cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&t_scratch.pinned), 64)) return cuda_fail(e, "cudaMallocHost");
+        if (cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&t_scratch.pinned), 128, cudaHostAllocMapped)) return cuda_fail(e, "cudaHostAlloc");
+        memset(t_scratch.pinned, 0, 128);
+        if (cudaError_t e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&t_scratch.pinned_dev), t_scratch.pinned, 0)) return cuda_fail(e, "cudaHostGetDevicePointer");
     }
     *out = t_scratch.pinned;
     return EC_OK;
@@ -179,7 +182,10 @@ static ec_status reduce_scratch(ReduceScratch* out) {
     const cudaStream_t s = cur_stream();
     for (auto& kv : t_scratch.per_stream)
         if (kv.first == s) { *out = kv.second; return EC_OK; }
-    ReduceScratch sc;
+    ReduceScratch sc{};
+    uint64_t* pin;
+    if (ec_status st = pinned_words(&pin)) return st;
+    sc.host_result = t_scratch.pinned_dev + 8;  // results land in pinned[8..11] without a D2H copy
     void* base = nullptr;
     const size_t bytes = (2 * kMaxReduceBlocks + 4 + 2) * sizeof(uint64_t);
     if (cudaError_t e = cudaMalloc(&base, bytes)) return cuda_fail(e, "cudaMalloc(reduce scratch)");
@@ -531,12 +537,43 @@ static ec_status ensure_unique(ec_buf* b) {
     return EC_OK;
 }
 
+// host side of a reduction whose finishing CTA wrote {r0, r1, epoch, status} into pinned[8..11]
+static ec_status reduce_result(uint64_t* r0, uint64_t* r1) {
+    EC_TRY(sync_stream());
+    volatile uint64_t* pin = t_scratch.pinned + 8;
+    *r0 = pin[0];
+    *r1 = pin[1];
+    if (pin[3] != 0) { set_error("a peer GPU did not deliver its partial result within the spin limit"); return EC_NCCL; }
+    return EC_OK;
+}
 // reduce a buffer to {min_key, max_key} (device, in scratch.result)
 static ec_status run_min_max(const ec_buf* b, const ec_mask* m, ReduceScratch* sc) {
     EC_TRY(resolve(b));
     EC_TRY(reduce_scratch(sc));
     EC_LAUNCH(launch_min_max(launch_ctx(), b->ct, rd(b), m ? m->words : nullptr, b->len, *sc), "min_max");
     return EC_OK;
+}
+
+// Sharded reductions finished inside the kernel over NVLink peer memory (see PeerExchange in ec_reduce.cuh).
+// An empty strip still takes part in the exchange: its kernel runs over zero cells and contributes the seeds / zero.
+ec_status reduce_min_max_peer(const ec_buf* b, const ec_mask* m, const PeerExchange& px, uint64_t* k0, uint64_t* k1) {
+    EC_TRY(ensure());
+    if (m && m->len != b->len) { set_error("Mask and buffer must have the same length."); return EC_LEN_MISMATCH; }
+    EC_TRY(resolve(b));
+    ReduceScratch sc;
+    EC_TRY(reduce_scratch(&sc));
+    sc.px = px;
+    EC_LAUNCH(launch_min_max(launch_ctx(), b->ct, rd(b), m ? m->words : nullptr, b->len, sc), "min_max(peer exchange)");
+    return reduce_result(k0, k1);
+}
+ec_status reduce_popcount_peer(const ec_mask* m, const PeerExchange& px, uint64_t* ones, uint64_t* len_sum) {
+    EC_TRY(ensure());
+    ReduceScratch sc;
+    EC_TRY(reduce_scratch(&sc));
+    sc.px = px;
+    // second word of the pair carries this strip's length so every rank also learns the total
+    EC_LAUNCH(launch_popcount(launch_ctx(), m->words, (m->len + 31) / 32, sc, m->len), "mask_counts(peer exchange)");
+    return reduce_result(ones, len_sum);
 }
 
 }  // namespace ec
@@ -988,12 +1025,7 @@ ec_status ec_buf_min_max(const ec_buf* b, const ec_mask* m, ec_value* mn, ec_val
     if (b->len) {
         ReduceScratch sc;
         EC_TRY(run_min_max(b, m, &sc));
-        uint64_t* pin;
-        EC_TRY(pinned_words(&pin));
-        EC_CUDA_TRY(cudaMemcpyAsync(pin, sc.result, 16, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
-        EC_TRY(sync_stream());
-        k[0] = pin[0];
-        k[1] = pin[1];
+        EC_TRY(reduce_result(&k[0], &k[1]));
     }
     *mn = tagged<uint64_t>(b->ct, key_to_bits(b->ct, k[0]));
     *mx = tagged<uint64_t>(b->ct, key_to_bits(b->ct, k[1]));
@@ -1009,11 +1041,8 @@ ec_status ec_buf_cmp(const ec_buf* l, const ec_buf* r, int* ordering) {
         ReduceScratch sc;
         EC_TRY(reduce_scratch(&sc));
         EC_LAUNCH(launch_first_diff(launch_ctx(), (int)kSize[l->ct], rd(l), rd(r), n, sc), "first_diff");
-        uint64_t* pin;
-        EC_TRY(pinned_words(&pin));
-        EC_CUDA_TRY(cudaMemcpyAsync(pin, sc.result, 16, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
-        EC_TRY(sync_stream());
-        const uint64_t idx = pin[0];
+        uint64_t idx, unused;
+        EC_TRY(reduce_result(&idx, &unused));
         if (idx != ~0ull) {
             ec_value a, b;
             EC_TRY(ec_buf_get(l, idx, &a));
@@ -1167,7 +1196,7 @@ ec_status ec_mask_and(const ec_mask* l, const ec_mask* r, ec_mask** out) { retur
 ec_status ec_mask_or(const ec_mask* l, const ec_mask* r, ec_mask** out) { return mask_bitop(2, l, r, out); }
 static ec_status mask_popcount_device(const ec_mask* m, ReduceScratch* sc) {
     EC_TRY(reduce_scratch(sc));
-    EC_LAUNCH(launch_popcount(launch_ctx(), m->words, (m->len + 31) / 32, *sc), "mask_counts");
+    EC_LAUNCH(launch_popcount(launch_ctx(), m->words, (m->len + 31) / 32, *sc, 0), "mask_counts");
     return EC_OK;
 }
 ec_status ec_mask_counts(const ec_mask* m, size_t* data, size_t* nodata) {
@@ -1176,11 +1205,8 @@ ec_status ec_mask_counts(const ec_mask* m, size_t* data, size_t* nodata) {
     if (m->len) {
         ReduceScratch sc;
         EC_TRY(mask_popcount_device(m, &sc));
-        uint64_t* pin;
-        EC_TRY(pinned_words(&pin));
-        EC_CUDA_TRY(cudaMemcpyAsync(pin, sc.result, 16, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
-        EC_TRY(sync_stream());
-        ones = pin[0];
+        uint64_t unused;
+        EC_TRY(reduce_result(&ones, &unused));
     }
     *data = ones;
     *nodata = m->len - ones;
@@ -1199,11 +1225,8 @@ ec_status ec_mask_cmp(const ec_mask* l, const ec_mask* r, int* ordering) {
         ReduceScratch sc;
         EC_TRY(reduce_scratch(&sc));
         EC_LAUNCH(launch_first_diff(launch_ctx(), 4, l->words, r->words, (n + 31) / 32, sc), "first_diff");
-        uint64_t* pin;
-        EC_TRY(pinned_words(&pin));
-        EC_CUDA_TRY(cudaMemcpyAsync(pin, sc.result, 16, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
-        EC_TRY(sync_stream());
-        const uint64_t w = pin[0];
+        uint64_t w, unused;
+        EC_TRY(reduce_result(&w, &unused));
         if (w != ~0ull) {
             uint32_t a, b;
             EC_TRY(mask_word(l, w, &a));

@@ -10,12 +10,19 @@
 #include <mutex>
 
 #include "ec_internal.hpp"
+#include "ec_reduce.cuh"
 
 struct ec_comm {
     ncclComm_t comm;
     int n_ranks, rank;
-    int64_t* dkeys;   // 2 device words for in-place all-reduce
+    int64_t* dkeys;   // 4 device words for in-place all-reduce
     int64_t* pinned;  // host mirror
+    // NVLink peer exchange (see PeerExchange in ec_reduce.cuh): every rank's mailbox mapped into every rank
+    bool peer_ok;
+    unsigned long long* mailbox;            // ours: 2 epochs x n_ranks slots x 4 words
+    unsigned long long** peer_ptrs_dev;     // device array [n_ranks]
+    void* opened[64];                       // cudaIpcOpenMemHandle mappings to close
+    unsigned long long epoch;
 };
 
 namespace ec {
@@ -25,6 +32,7 @@ struct Nccl {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 static Nccl g_nccl;
@@ -46,6 +54,7 @@ static ec_status nccl_load() {
     SYM(CommInitRank, "ncclCommInitRank")
     SYM(CommDestroy, "ncclCommDestroy")
     SYM(AllReduce, "ncclAllReduce")
+    SYM(AllGather, "ncclAllGather")
     SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
     g_nccl.h = h;
@@ -69,9 +78,61 @@ ec_status ec_comm_unique_id(void* id128) {
     memcpy(id128, &id, 128);
     return EC_OK;
 }
+// Map every rank's mailbox into this process: cudaIpc handles travel through an NCCL all-gather.
+static ec_status peer_setup(ec_comm* c) {
+    c->peer_ok = false;
+    if (c->n_ranks > 32 || env_int("EC_NO_PEER_EXCHANGE", 0)) return EC_OK;  // one warp folds the ranks; NCCL path otherwise
+    cudaStream_t st = static_cast<cudaStream_t>(ec_get_stream());
+    const size_t words = size_t(2) * c->n_ranks * 4;
+    if (cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->mailbox), words * 8)) return cuda_fail(e, "cudaMalloc(mailbox)");
+    if (cudaError_t e = cudaMemset(c->mailbox, 0, words * 8)) return cuda_fail(e, "cudaMemset(mailbox)");
+    cudaIpcMemHandle_t mine;
+    if (cudaIpcGetMemHandle(&mine, c->mailbox) != cudaSuccess) { cudaGetLastError(); return EC_OK; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    char* dh = nullptr;
+    if (cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&dh), size_t(64) * (c->n_ranks + 1))) return cuda_fail(e, "cudaMalloc");
+    if (cudaError_t e = cudaMemcpyAsync(dh, &mine, 64, cudaMemcpyHostToDevice, st)) return cuda_fail(e, "cudaMemcpyAsync");
+    if (ncclResult_t r = g_nccl.AllGather(dh, dh + 64, 64, ncclChar, c->comm, st)) return nccl_fail(r, "ncclAllGather(ipc handles)");
+    cudaIpcMemHandle_t all[64];
+    if (cudaError_t e = cudaMemcpyAsync(all, dh + 64, size_t(64) * c->n_ranks, cudaMemcpyDeviceToHost, st)) return cuda_fail(e, "cudaMemcpyAsync");
+    if (cudaError_t e = cudaStreamSynchronize(st)) return cuda_fail(e, "cudaStreamSynchronize");
+    cudaFree(dh);
+    unsigned long long* ptrs[64];
+    int ok = 1;
+    for (int r = 0; r < c->n_ranks; ++r) {
+        c->opened[r] = nullptr;
+        if (r == c->rank) { ptrs[r] = c->mailbox; continue; }
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        c->opened[r] = p;
+        ptrs[r] = static_cast<unsigned long long*>(p);
+    }
+    // every rank must agree before anyone uses the exchange (a rank that could not map a peer vetoes it)
+    c->pinned[0] = ok;
+    if (cudaError_t e = cudaMemcpyAsync(c->dkeys, c->pinned, 8, cudaMemcpyHostToDevice, st)) return cuda_fail(e, "cudaMemcpyAsync");
+    if (ncclResult_t r = g_nccl.AllReduce(c->dkeys, c->dkeys, 1, ncclInt64, ncclMin, c->comm, st)) return nccl_fail(r, "ncclAllReduce");
+    if (cudaError_t e = cudaMemcpyAsync(c->pinned, c->dkeys, 8, cudaMemcpyDeviceToHost, st)) return cuda_fail(e, "cudaMemcpyAsync");
+    if (cudaError_t e = cudaStreamSynchronize(st)) return cuda_fail(e, "cudaStreamSynchronize");
+    if (c->pinned[0] != 1) return EC_OK;
+    if (cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->peer_ptrs_dev), sizeof(void*) * c->n_ranks)) return cuda_fail(e, "cudaMalloc");
+    if (cudaError_t e = cudaMemcpy(c->peer_ptrs_dev, ptrs, sizeof(void*) * c->n_ranks, cudaMemcpyHostToDevice)) return cuda_fail(e, "cudaMemcpy");
+    c->peer_ok = true;
+    return EC_OK;
+}
+static PeerExchange next_exchange(ec_comm* c) {
+    PeerExchange px;
+    px.peers = c->peer_ptrs_dev;
+    px.n_ranks = c->n_ranks;
+    px.rank = c->rank;
+    px.epoch = ++c->epoch;
+    px.spin_limit = 4000000000ull;  // ~2 s of SM clocks: a missing peer turns into an error, not a hang
+    return px;
+}
+
 ec_status ec_comm_init_rank(const void* id128, int n_ranks, int rank, ec_comm** out) {
     if (ec_status s = nccl_load()) return s;
     if (ec_status s = ec_synchronize()) return s;  // binds the device
+    if (n_ranks < 1 || n_ranks > 64 || rank < 0 || rank >= n_ranks) { set_error("invalid argument: rank / n_ranks"); return EC_INVALID_ARG; }
     ncclUniqueId id;
     memcpy(&id, id128, 128);
     ec_comm* c = new ec_comm{};
@@ -80,12 +141,18 @@ ec_status ec_comm_init_rank(const void* id128, int n_ranks, int rank, ec_comm** 
     if (ncclResult_t r = g_nccl.CommInitRank(&c->comm, n_ranks, id, rank)) { delete c; return nccl_fail(r, "ncclCommInitRank"); }
     if (cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->dkeys), 4 * sizeof(int64_t))) { delete c; return cuda_fail(e, "cudaMalloc"); }
     if (cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&c->pinned), 4 * sizeof(int64_t))) { delete c; return cuda_fail(e, "cudaMallocHost"); }
+    if (ec_status s = peer_setup(c)) { ec_comm_destroy(c); return s; }
     *out = c;
     return EC_OK;
 }
+int ec_comm_peer_exchange(const ec_comm* c) { return c->peer_ok ? 1 : 0; }
 void ec_comm_destroy(ec_comm* c) {
     if (!c) return;
+    for (int r = 0; r < c->n_ranks && r < 64; ++r)
+        if (c->opened[r]) cudaIpcCloseMemHandle(c->opened[r]);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    cudaFree(c->peer_ptrs_dev);
+    cudaFree(c->mailbox);
     cudaFree(c->dkeys);
     cudaFreeHost(c->pinned);
     delete c;
@@ -101,6 +168,16 @@ ec_status ec_comm_allreduce_sum_u64(ec_comm* c, uint64_t* device_buf, size_t cou
     return EC_OK;
 }
 ec_status ec_buf_min_max_sharded(ec_comm* c, const ec_buf* shard, const ec_mask* mask_or_null, ec_value* mn, ec_value* mx) {
+    if (c->peer_ok) {  // ONE kernel per GPU: shard reduction + exchange over NVLink peer memory + final fold
+        uint64_t k[2];
+        if (ec_status s = reduce_min_max_peer(shard, mask_or_null, next_exchange(c), &k[0], &k[1])) return s;
+        const uint8_t ct = ec_buf_ctype(shard);
+        memset(mn, 0, sizeof *mn); memset(mx, 0, sizeof *mx);
+        mn->ct = mx->ct = ct;
+        mn->bits = key_to_bits(ct, k[0]);
+        mx->bits = key_to_bits(ct, k[1]);
+        return EC_OK;
+    }
     if (ec_status s = ec_buf_min_max_keys(shard, mask_or_null, c->dkeys)) return s;
     if (ec_status s = ec_comm_allreduce_min_i64(c, c->dkeys, 2)) return s;
     cudaStream_t st = static_cast<cudaStream_t>(ec_get_stream());
@@ -109,6 +186,13 @@ ec_status ec_buf_min_max_sharded(ec_comm* c, const ec_buf* shard, const ec_mask*
     return ec_min_max_from_keys(ec_buf_ctype(shard), c->pinned, mn, mx);
 }
 ec_status ec_mask_counts_sharded(ec_comm* c, const ec_mask* shard, size_t* data, size_t* nodata) {
+    if (c->peer_ok) {
+        uint64_t ones, total;
+        if (ec_status s = reduce_popcount_peer(shard, next_exchange(c), &ones, &total)) return s;
+        *data = ones;
+        *nodata = total - ones;
+        return EC_OK;
+    }
     size_t d = 0, nd = 0;
     if (ec_status s = ec_mask_counts(shard, &d, &nd)) return s;
     cudaStream_t st = static_cast<cudaStream_t>(ec_get_stream());

@@ -36,6 +36,7 @@ struct ec_event {
 namespace ec {
 
 struct ReduceScratch;
+struct PeerExchange;
 
 struct Launch {  // launch context handed to every launcher
     cudaStream_t stream;
@@ -74,7 +75,9 @@ cudaError_t launch_binary_scalar(const Launch& L, int op1, int lct, const void* 
 // reductions: results land in scratch.result[0..1] (device); keys are unsigned order keys
 cudaError_t launch_min_max(const Launch& L, int ct, const void* a, const uint32_t* mask, size_t n,
                            const ReduceScratch& s);
-cudaError_t launch_popcount(const Launch& L, const uint32_t* words, size_t nwords, const ReduceScratch& s);
+cudaError_t launch_popcount(const Launch& L, const uint32_t* words, size_t nwords, const ReduceScratch& s, uint64_t second_word);
+ec_status reduce_min_max_peer(const ec_buf* b, const ec_mask* m, const PeerExchange& px, uint64_t* k0, uint64_t* k1);
+ec_status reduce_popcount_peer(const ec_mask* m, const PeerExchange& px, uint64_t* ones, uint64_t* len_sum);
 cudaError_t launch_first_diff(const Launch& L, int cell_bytes, const void* a, const void* b, size_t n,
                               const ReduceScratch& s);
 // masks

@@ -12,10 +12,25 @@
 
 namespace ec {
 
+// Cross-GPU finish over NVLink peer memory (row-strip sharding, one rank per GPU). When `peers` is set, the CTA
+// that folds this GPU's partials also exchanges the 16-byte partial result with every peer — remote stores into
+// each peer's mailbox, then a bounded spin on its own mailbox — and reduces the n_ranks pairs, so a sharded
+// reduction is ONE kernel per GPU with no separate collective launch. Mailbox slot (32 bytes) of sender r for
+// epoch e lives at word 4 * ((e & 1) * n_ranks + r): {value0, value1, epoch, pad}. Two epochs of slots suffice:
+// a rank can only be one collective ahead of the slowest peer, because finishing epoch e needs every peer's
+// epoch-e message.
+struct PeerExchange {
+    unsigned long long* const* peers;  // device array [n_ranks]: every rank's mailbox, peer-mapped (null = single GPU)
+    int n_ranks, rank;
+    unsigned long long epoch;          // >= 1, identical on all ranks for one collective
+    unsigned long long spin_limit;     // clock64() ticks before giving up on a peer
+};
 struct ReduceScratch {
     uint64_t* partials;     // 2 * max_blocks
     unsigned int* ticket;   // zero between launches (the finishing CTA resets it)
     uint64_t* result;       // 4 words: [0..1] raw result; [2..3] min_max as {skey(min), ~skey(max)} for a MIN all-reduce
+    uint64_t* host_result;  // optional device alias of mapped pinned host memory: {r0, r1, epoch or 1, status}; saves the D2H copy
+    PeerExchange px;
 };
 
 __device__ __forceinline__ uint32_t warp_min(uint32_t v) { return __reduce_min_sync(0xFFFFFFFFu, v); }
@@ -75,15 +90,61 @@ __device__ __forceinline__ void block_finish(uint64_t k0, uint64_t k1, uint64_t 
     __syncthreads();
     if (lane == 0) { sh0[warp] = a0; sh1[warp] = a1; }
     __syncthreads();
+    __shared__ uint64_t xr[2];
+    __shared__ unsigned int xstatus;
     if (threadIdx.x == 0) {
         a0 = sh0[0]; a1 = sh1[0];
 #pragma unroll
         for (int w = 1; w < THREADS / 32; ++w) combine<MODE>(a0, a1, sh0[w], sh1[w]);
+        xr[0] = a0; xr[1] = a1;
+        xstatus = 0;
+    }
+    if (s.px.peers != nullptr) {
+        // ---- exchange with the peer GPUs (uniform branch: every thread of the CTA takes it) ----
+        __syncthreads();
+        const int n = s.px.n_ranks;
+        const unsigned long long base = 4ull * ((s.px.epoch & 1ull) * n);
+        if (threadIdx.x < n) {  // thread t talks to rank t: send ...
+            volatile unsigned long long* slot = s.px.peers[threadIdx.x] + base + 4ull * s.px.rank;
+            slot[0] = xr[0];
+            slot[1] = xr[1];
+            __threadfence_system();
+            slot[2] = s.px.epoch;
+        }
+        uint64_t p0 = id0, p1 = id1;
+        if (threadIdx.x < n) {  // ... then receive rank t's partial from our own mailbox
+            volatile unsigned long long* slot = s.px.peers[s.px.rank] + base + 4ull * threadIdx.x;
+            const long long t0 = clock64();
+            bool ok = true;
+            while (slot[2] != s.px.epoch) {
+                if (static_cast<unsigned long long>(clock64() - t0) > s.px.spin_limit) { ok = false; break; }
+            }
+            __threadfence_system();
+            if (ok) { p0 = slot[0]; p1 = slot[1]; } else { atomicOr(&xstatus, 1u); }
+        }
+        // fold the n_ranks pairs (n_ranks <= 32: one warp)
+        if (threadIdx.x < 32) {
+            if constexpr (MODE == RED_MINMAX) { p0 = warp_min(p0); p1 = warp_max(p1); }
+            else if constexpr (MODE == RED_SUM) { p0 = warp_sum(p0); p1 = warp_sum(p1); }
+            else { p0 = warp_min(p0); p1 = warp_min(p1); }
+            if (threadIdx.x == 0) { xr[0] = p0; xr[1] = p1; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        a0 = xr[0]; a1 = xr[1];
         s.result[0] = a0;
         s.result[1] = a1;
         if constexpr (MODE == RED_MINMAX) {  // order-preserving signed keys, max negated
             s.result[2] = a0 ^ 0x8000000000000000ull;
             s.result[3] = ~(a1 ^ 0x8000000000000000ull);
+        }
+        if (s.host_result != nullptr) {  // mapped pinned memory: the host reads it after a stream sync, no D2H copy
+            s.host_result[0] = a0;
+            s.host_result[1] = a1;
+            s.host_result[3] = xstatus;
+            __threadfence_system();
+            s.host_result[2] = s.px.peers != nullptr ? s.px.epoch : 1ull;
         }
         *s.ticket = 0;  // ready for the next launch on this stream
     }
@@ -183,7 +244,8 @@ __global__ void __launch_bounds__(THREADS) min_max_kernel(const T* __restrict__ 
 
 // ---- Mask::counts: popcount over packed words (tail bits beyond len are kept zero) ---------------
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) popcount_kernel(const uint32_t* __restrict__ m, size_t words, ReduceScratch s) {
+__global__ void __launch_bounds__(THREADS) popcount_kernel(const uint32_t* __restrict__ m, size_t words, ReduceScratch s,
+                                                           uint64_t second_word) {
     uint64_t c = 0;
     const size_t groups = words / 4;  // 16-byte groups (allocation is padded to 16 bytes, pad is zero)
     for (size_t g = blockIdx.x * size_t(THREADS) + threadIdx.x; g < groups; g += size_t(gridDim.x) * THREADS) {
@@ -192,7 +254,8 @@ __global__ void __launch_bounds__(THREADS) popcount_kernel(const uint32_t* __res
     }
     if (blockIdx.x == 0 && threadIdx.x < words % 4) c += __popc(m[groups * 4 + threadIdx.x]);
     c = warp_sum(c);
-    block_finish<RED_SUM, THREADS>(c, 0, 0, 0, s);
+    // the second word of the pair is a caller-supplied constant (the strip length for sharded counts), added once
+    block_finish<RED_SUM, THREADS>(c, (blockIdx.x == 0 && threadIdx.x == 0) ? second_word : 0, 0, 0, s);
 }
 
 // ---- first differing cell of two buffers of the same type (bitwise == total-order equality) -------

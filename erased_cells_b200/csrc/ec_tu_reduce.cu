@@ -84,9 +84,9 @@ uint64_t key_from_bits(int ct, uint64_t bits) {
 int64_t key_to_signed(uint64_t key) { return static_cast<int64_t>(key ^ 0x8000000000000000ull); }
 uint64_t key_from_signed(int64_t skey) { return static_cast<uint64_t>(skey) ^ 0x8000000000000000ull; }
 
-cudaError_t launch_popcount(const Launch& Lc, const uint32_t* words, size_t nwords, const ReduceScratch& s) {
+cudaError_t launch_popcount(const Launch& Lc, const uint32_t* words, size_t nwords, const ReduceScratch& s, uint64_t second_word) {
     const int grid = reduce_grid(nwords / 4, kThreads, Lc);
-    popcount_kernel<kThreads><<<grid, kThreads, 0, Lc.stream>>>(words, nwords, s);
+    popcount_kernel<kThreads><<<grid, kThreads, 0, Lc.stream>>>(words, nwords, s, second_word);
     return cudaGetLastError();
 }
 

@@ -61,3 +61,48 @@ def counts_sharded(mask: Mask, group=None) -> tuple[int, int]:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return int(t[0]), int(t[1])
+
+
+class Comm:
+    """The library's own communicator (ec_comm_*): NCCL for plumbing, and — when every rank can map every other rank's
+    mailbox over NVLink — sharded reductions as ONE kernel per GPU (reduction + peer exchange + final fold)."""
+
+    def __init__(self, handle, n_ranks, rank):
+        self._h, self.n_ranks, self.rank = handle, n_ranks, rank
+
+    @staticmethod
+    def create(group=None) -> "Comm":
+        """Rank 0 draws the NCCL unique id; it travels through torch.distributed (any backend)."""
+        import torch
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        raw = (C.c_uint8 * 128)()
+        if rank == 0:
+            check(lib().ec_comm_unique_id(raw))
+        t = torch.tensor(list(raw), dtype=torch.uint8)
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, 0, group=group)
+        raw = (C.c_uint8 * 128)(*t.cpu().tolist())
+        h = C.c_void_p()
+        check(lib().ec_comm_init_rank(raw, world, rank, C.byref(h)))
+        return Comm(h.value, world, rank)
+
+    @property
+    def peer_exchange(self) -> bool:
+        return bool(lib().ec_comm_peer_exchange(self._h))
+
+    def min_max(self, shard: CellBuffer, mask: Mask | None = None) -> tuple[CellValue, CellValue]:
+        mn, mx = Value(), Value()
+        check(lib().ec_buf_min_max_sharded(self._h, shard._h, mask._h if mask is not None else None, C.byref(mn), C.byref(mx)))
+        return CellValue._wrap(mn), CellValue._wrap(mx)
+
+    def counts(self, mask: Mask) -> tuple[int, int]:
+        d, n = C.c_size_t(), C.c_size_t()
+        check(lib().ec_mask_counts_sharded(self._h, mask._h, C.byref(d), C.byref(n)))
+        return d.value, n.value
+
+    def close(self):
+        if self._h:
+            lib().ec_comm_destroy(self._h)
+            self._h = None

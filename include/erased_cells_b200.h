@@ -239,6 +239,10 @@ ec_status ec_min_max_to_keys(const ec_value* min_in, const ec_value* max_in, int
 ec_status ec_comm_unique_id(void* id128);  /* 128 bytes, created on rank 0 and shipped by the host */
 ec_status ec_comm_init_rank(const void* id128, int n_ranks, int rank, ec_comm** out);
 void ec_comm_destroy(ec_comm* c);
+/* 1 when every rank could map every other rank's mailbox (cudaIpc over NVLink): the sharded reductions below then
+ * run as ONE kernel per GPU — shard reduction, exchange of the 16-byte partials through peer memory and the final
+ * fold in the finishing CTA — instead of kernel + NCCL all-reduce + copy. 0: the NCCL path is used. */
+int ec_comm_peer_exchange(const ec_comm* c);
 ec_status ec_comm_allreduce_min_i64(ec_comm* c, int64_t* device_buf, size_t count);
 ec_status ec_comm_allreduce_sum_u64(ec_comm* c, uint64_t* device_buf, size_t count);
 /* sharded min_max / counts: shard-local kernel + one all-reduce, result on every rank */

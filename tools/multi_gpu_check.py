@@ -27,16 +27,10 @@ W = H = int(os.environ.get("EC_SIDE", 16384))
 off, ln = sharding.row_strip(W, H, world, rank)
 
 # --- the library's own communicator: unique id from rank 0, shipped with torch.distributed ----------
-idbuf = torch.zeros(128, dtype=torch.uint8)
+comm_obj = sharding.Comm.create()
+comm = C.c_void_p(comm_obj._h)
 if rank == 0:
-    raw = (C.c_uint8 * 128)()
-    ec._lib.check(L.ec_comm_unique_id(raw))
-    idbuf = torch.tensor(list(raw), dtype=torch.uint8)
-idbuf = idbuf.cuda()
-dist.broadcast(idbuf, 0)
-raw = (C.c_uint8 * 128)(*idbuf.cpu().tolist())
-comm = C.c_void_p()
-ec._lib.check(L.ec_comm_init_rank(raw, world, rank, C.byref(comm)))
+    print("peer exchange over NVLink (fused one-kernel sharded reductions):", comm_obj.peer_exchange)
 
 ok = True
 for ct in (CellType.Float32, CellType.Int16, CellType.UInt8, CellType.Float64, CellType.UInt64):
@@ -62,9 +56,24 @@ for ct in (CellType.Float32, CellType.Int16, CellType.UInt8, CellType.Float64, C
     ok &= good
     del whole, strip, ms, mw
 
+# latency of the two ways to finish a sharded f32 min_max (device events around 50 calls)
+strip = synth.device(CellType.Float32, ln, 0xEC40, index_offset=off, kind=synth.REAL_RANGE, lo=-1e4, hi=1e4)
+for label, fn in (("torch.distributed NCCL all-reduce", lambda: sharding.min_max_sharded(strip)), ("ec_comm (peer exchange in the kernel)" if comm_obj.peer_exchange else "ec_comm (NCCL)", lambda: comm_obj.min_max(strip))):
+    for _ in range(5):
+        fn()
+    dist.barrier(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(50):
+        fn()
+    b.record(); torch.cuda.synchronize()
+    if rank == 0:
+        print(f"sharded f32 min_max of {W}x{H} over {world} GPUs, {label}: {a.elapsed_time(b) / 50 * 1e3:.1f} us per call")
+del strip
+
 t = torch.tensor([int(ok)], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
-L.ec_comm_destroy(comm)
+comm_obj.close()
 dist.destroy_process_group()
 if rank == 0:
     print("MULTI_GPU_OK" if int(t.item()) else "MULTI_GPU_FAILED")
