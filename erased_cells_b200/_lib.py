@@ -77,6 +77,7 @@ def _signatures():
         "ec_get_stream": (VP, []),
         "ec_synchronize": (S, []),
         "ec_trim": (S, []),
+        "ec_guard_violations": (U64, []),
         "ec_cached_bytes": (SZ, []),
         "ec_set_lazy": (S, [I]),
         "ec_get_lazy": (I, []),
@@ -108,6 +109,7 @@ def _signatures():
         "ec_value_to_f64": (S, [PV, C.POINTER(C.c_double), PI]),
         "ec_value_to_i64": (S, [PV, C.POINTER(I64), PI]),
         "ec_value_to_u64": (S, [PV, C.POINTER(U64), PI]),
+        "ec_value_to_prim": (S, [PV, U8, PV, PI]),
         "ec_buf_from_host": (S, [U8, VP, SZ, PVP]),
         "ec_buf_from_host_async": (S, [U8, VP, SZ, PVP]),
         "ec_buf_wait": (S, [VP]),

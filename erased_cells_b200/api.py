@@ -166,6 +166,12 @@ class CellValue:
         check(lib().ec_value_to_u64(C.byref(self._v), C.byref(o), C.byref(some)))
         return o.value if some.value else None
 
+    def to_prim(self, cell_type: CellType):
+        """`self.to_<p>()`: value-checked ToPrimitive chain; None where the reference yields None."""
+        out, some = Value(), C.c_int()
+        check(lib().ec_value_to_prim(C.byref(self._v), int(cell_type), C.byref(out), C.byref(some)))
+        return CellValue._wrap(out) if some.value else None
+
     def _bin(self, op, rhs):
         r = _into_value(rhs)
         out = Value()

@@ -126,9 +126,46 @@ static void cache_release_all_locked() {
     g_cache.free_by_stream.clear();
     g_cache.cached_bytes = 0;
 }
+// EC_DEBUG_GUARD=1 (compute-sanitizer is not available on every pool): every block gets 256-byte red zones
+// directly before its first and after its last requested byte, filled with 0xA5 and verified when the block is
+// freed; no caching in this mode. ec_guard_violations() reports how many zones were found overwritten.
+static bool g_guard = false;
+static std::atomic<uint64_t> g_guard_violations{0};
+static std::map<void*, std::pair<void*, size_t>> g_guard_live;  // user ptr -> (real ptr, requested bytes)
+constexpr size_t kGuard = 256;
+static ec_status guard_alloc(void** p, size_t bytes) {
+    void* real = nullptr;
+    if (cudaError_t e = cudaMalloc(&real, bytes + 2 * kGuard)) return cuda_fail(e, "cudaMalloc");
+    char* user = static_cast<char*>(real) + kGuard;
+    cudaMemsetAsync(real, 0xA5, kGuard, cur_stream());
+    cudaMemsetAsync(user + bytes, 0xA5, kGuard, cur_stream());
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    g_guard_live[user] = {real, bytes};
+    *p = user;
+    return EC_OK;
+}
+static bool guard_free(void* p) {
+    std::pair<void*, size_t> rec;
+    {
+        std::lock_guard<std::mutex> lk(g_cache.mu);
+        auto it = g_guard_live.find(p);
+        if (it == g_guard_live.end()) return false;
+        rec = it->second;
+        g_guard_live.erase(it);
+    }
+    unsigned char zones[2 * kGuard];
+    cudaStreamSynchronize(cur_stream());
+    cudaMemcpy(zones, rec.first, kGuard, cudaMemcpyDeviceToHost);
+    cudaMemcpy(zones + kGuard, static_cast<char*>(p) + rec.second, kGuard, cudaMemcpyDeviceToHost);
+    for (size_t i = 0; i < 2 * kGuard; ++i)
+        if (zones[i] != 0xA5) { g_guard_violations.fetch_add(1); fprintf(stderr, "erased_cells_b200: red zone of a %zu-byte block overwritten at %s%zu\n", rec.second, i < kGuard ? "-" : "+", i < kGuard ? kGuard - i : i - kGuard); break; }
+    cudaFree(rec.first);
+    return true;
+}
 static ec_status dev_alloc(void** p, size_t bytes) {
     *p = nullptr;
     if (bytes == 0) return EC_OK;
+    if (g_guard) return guard_alloc(p, bytes);
     bytes = round_block(bytes);
     std::lock_guard<std::mutex> lk(g_cache.mu);
     auto& fl = g_cache.free_by_stream[cur_stream()];
@@ -152,6 +189,7 @@ static ec_status dev_alloc(void** p, size_t bytes) {
 }
 static void dev_free(void* p) {
     if (!p) return;
+    if (g_guard && guard_free(p)) return;
     std::lock_guard<std::mutex> lk(g_cache.mu);
     auto it = g_cache.live.find(p);
     if (it == g_cache.live.end()) return;
@@ -607,6 +645,7 @@ ec_status ec_init(int device) {
     EC_CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.own, cudaStreamNonBlocking), "cudaStreamCreate");
     EC_CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.upload, cudaStreamNonBlocking), "cudaStreamCreate");
     g_ctx.max_grid = env_int("EC_MAX_GRID", 0);
+    g_guard = env_int("EC_DEBUG_GUARD", 0) != 0;
     g_ctx.device = device;
     g_ctx.inited = true;
     t_device_bound = true;
@@ -646,6 +685,7 @@ size_t ec_cached_bytes(void) {
     std::lock_guard<std::mutex> lk(g_cache.mu);
     return g_cache.cached_bytes;
 }
+uint64_t ec_guard_violations(void) { return g_guard_violations.load(); }
 ec_status ec_set_lazy(int on) {
     t_lazy = on != 0;
     return EC_OK;
@@ -773,6 +813,37 @@ ec_status ec_value_to_u64(const ec_value* v, uint64_t* out, int* is_some) {
         *is_some = (w.f > -1.0 && w.f < 18446744073709551616.0);
         *out = *is_some ? (uint64_t)w.f : 0;
     } else { *is_some = !w.is_neg_int; *out = *is_some ? w.u : 0; }
+    return EC_OK;
+}
+
+// `self.to_<p>()` on a CellValue (src/value.rs:92 call shape; also Extend, src/buffer.rs:212, and the GDAL nodata
+// conversion, src/gdal/mod.rs:59): the VALUE-checked num-traits chain — ints through i64/u64 with range checks,
+// floats truncated iff inside the target's range, anything -> f32 through f64.
+ec_status ec_value_to_prim(const ec_value* v, uint8_t ct, ec_value* out, int* is_some) {
+    if (!ct_ok(v->ct) || !ct_ok(ct)) return invalid("cell type");
+    const Widened w = widen(*v);
+    *is_some = 1;
+    if (ct == EC_FLOAT64) { *out = tagged<double>(ct, value_as_f64(*v)); return EC_OK; }
+    if (ct == EC_FLOAT32) { *out = tagged<float>(ct, (float)value_as_f64(*v)); return EC_OK; }
+    if (ct_signed(ct)) {
+        int64_t t = 0;
+        int some = 0;
+        EC_TRY(ec_value_to_i64(v, &t, &some));
+        const int bits = int(kSize[ct]) * 8;
+        const int64_t hi = bits == 64 ? std::numeric_limits<int64_t>::max() : (int64_t(1) << (bits - 1)) - 1, lo = -hi - 1;
+        if (!some || t < lo || t > hi) { *is_some = 0; return EC_OK; }
+        *out = tagged<int64_t>(ct, t);
+        out->bits &= bits == 64 ? ~0ull : ((1ull << bits) - 1);
+        return EC_OK;
+    }
+    uint64_t t = 0;
+    int some = 0;
+    EC_TRY(ec_value_to_u64(v, &t, &some));
+    const int bits = int(kSize[ct]) * 8;
+    const uint64_t hi = bits == 64 ? ~0ull : ((1ull << bits) - 1);
+    if (!some || t > hi) { *is_some = 0; return EC_OK; }
+    *out = tagged<uint64_t>(ct, t);
+    (void)w;
     return EC_OK;
 }
 

@@ -104,6 +104,9 @@ ec_status ec_synchronize(void);
 /* Freed device blocks are cached per stream for reuse (outputs are fresh allocations on every op).
  * ec_trim() synchronises the current stream and returns all cached blocks to the driver. */
 ec_status ec_trim(void);
+/* With EC_DEBUG_GUARD=1 in the environment every device block carries 256-byte red zones checked on free;
+ * this is the number of zones found overwritten so far (0 when the mode is off). */
+uint64_t ec_guard_violations(void);
 size_t ec_cached_bytes(void);
 uint64_t ec_kernel_launches(void);       /* number of this library's kernels launched so far */
 /* name of the last kernel family launched by this thread (for profiles/bench bookkeeping) */
@@ -139,6 +142,9 @@ ec_status ec_value_cmp(const ec_value* l, const ec_value* r, int* ordering);    
 ec_status ec_value_to_f64(const ec_value* v, double* out, int* is_some);              /* :144-156 */
 ec_status ec_value_to_i64(const ec_value* v, int64_t* out, int* is_some);             /* :118-129 */
 ec_status ec_value_to_u64(const ec_value* v, uint64_t* out, int* is_some);            /* :131-142 */
+/* `self.to_<p>()`: the value-checked num-traits default chain (call sites src/value.rs:92, src/buffer.rs:212,
+ * src/gdal/mod.rs:59); *is_some = 0 is the reference's `None` */
+ec_status ec_value_to_prim(const ec_value* v, uint8_t ct, ec_value* out, int* is_some);
 
 /* ---- CellBuffer — src/buffer.rs ------------------------------------------------------------- */
 /* from_vec / From<Vec<T>> / From<&[T]> (:64-66, :252-276): one H2D copy of `len` cells */

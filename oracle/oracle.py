@@ -94,6 +94,7 @@ def lib():
             "eco_value_convert": (I, [PV, I, PV]),
             "eco_value_binary": (None, [I, PV, PV, PV]),
             "eco_value_neg": (None, [PV, PV]),
+            "eco_value_to_prim": (I, [PV, I, PV]),
             "eco_value_cmp": (I, [PV, PV]),
             "eco_value_to_f64": (I, [PV, C.POINTER(C.c_double)]),
             "eco_value_to_i64": (I, [PV, C.POINTER(C.c_int64)]),
@@ -188,6 +189,11 @@ def value_binary(op, l: Value, r: Value) -> Value:
 
 def value_neg(v: Value) -> Value:
     return _v(lib().eco_value_neg, C.byref(v))
+
+
+def value_to_prim(v: Value, ct: int):
+    o = Value()
+    return o if lib().eco_value_to_prim(C.byref(v), ct, C.byref(o)) else None
 
 
 def value_cmp(l: Value, r: Value) -> int:

@@ -52,6 +52,17 @@ int eco_value_convert(const eco_value* v, int ct, eco_value* o) {
 }
 void eco_value_binary(int op, const eco_value* l, const eco_value* r, eco_value* o) { *o = out(binary(Op(op), in(*l), in(*r))); }
 void eco_value_neg(const eco_value* v, eco_value* o) { *o = out(neg(in(*v))); }
+int eco_value_to_prim(const eco_value* v, int ct, eco_value* o) {  // default-chain to_<p>(); 0 = None
+    std::optional<CellValue> r;
+    switch (CellType(ct)) {
+#define X(id, p) case id: r = to_prim<p>(in(*v)); break;
+        ECO_WITH_CT(X)
+#undef X
+    }
+    if (!r) return 0;
+    *o = out(*r);
+    return 1;
+}
 int eco_value_cmp(const eco_value* l, const eco_value* r) { return cmp(in(*l), in(*r)); }
 int eco_value_to_f64(const eco_value* v, double* o) { auto r = to_f64(in(*v)); if (!r) return 1; *o = *r; return 0; }
 int eco_value_to_i64(const eco_value* v, int64_t* o) { auto r = to_i64(in(*v)); if (!r) return 1; *o = *r; return 0; }

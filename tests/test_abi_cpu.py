@@ -81,6 +81,11 @@ def test_scalar_ops_match_oracle(orc):
             assert (int(n.cell_type()), n.bits) == on.key()
             assert a.to_f64() == orc.value_to_f64(oa) or (np.isnan(a.to_f64()) and np.isnan(orc.value_to_f64(oa)))
             assert a.to_i64() == orc.value_to_i64(oa) and a.to_u64() == orc.value_to_u64(oa)
+            for d in CellType:  # value-checked to_<p>() (Extend / GDAL nodata conversion)
+                got, want = a.to_prim(d), orc.value_to_prim(oa, int(d))
+                assert (got is None) == (want is None), (lct, d, x)
+                if got is not None:
+                    assert (int(got.cell_type()), got.bits) == want.key(), (lct, d, x)
             for d in CellType:
                 if lct.can_fit_into(d):
                     c = a.convert(d)
