@@ -5,7 +5,7 @@ The product is ``lib/liberased_cells_b200.so`` (hand-written sm_100a kernels beh
 used by the parity tests and the bench. Nothing here computes cells on the CPU.
 """
 from ._lib import EcError, NarrowingError, NoDeviceError, ParseError, build, lib  # noqa: F401
-from .api import CellBuffer, CellType, CellValue, Mask, MaskedCellBuffer, NoData  # noqa: F401
+from .api import CellBuffer, CellType, CellValue, Mask, MaskedCellBuffer, NoData, from_serde, to_serde  # noqa: F401
 
 import contextlib as _contextlib
 

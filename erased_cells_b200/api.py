@@ -688,3 +688,51 @@ class MaskedCellBuffer:
 
 
 MaskedCellBuffer.new = staticmethod(lambda buffer, mask: MaskedCellBuffer(buffer, mask))
+
+
+# ---------------------------------------------------------------------------------------------
+# serde wire format: the derives of src/ctype.rs:15, src/value.rs:16, src/buffer.rs:51,
+# src/masked/mask.rs:11, src/masked/masked_buffer.rs:40, src/masked/nodata.rs:8 with serde's default
+# representations — externally tagged enums, newtype struct = inner value, tuple struct = sequence. The reference
+# holds no test for it (parity unpinned); this follows serde_json's documented behaviour, non-finite floats as null.
+# ---------------------------------------------------------------------------------------------
+def _jnum(x):
+    x = x.item() if hasattr(x, "item") else x
+    if isinstance(x, float) and (x != x or x in (float("inf"), float("-inf"))):
+        return None
+    return x
+
+
+def to_serde(obj):
+    """A JSON-ready python structure in serde's default layout."""
+    if isinstance(obj, CellType):
+        return str(obj)
+    if isinstance(obj, CellValue):
+        return {str(obj.cell_type()): _jnum(obj.value())}
+    if isinstance(obj, CellBuffer):
+        return {str(obj.cell_type()): [_jnum(x) for x in obj.to_vec()]}
+    if isinstance(obj, Mask):
+        return [bool(b) for b in obj.to_vec()]
+    if isinstance(obj, MaskedCellBuffer):
+        return [to_serde(obj.buffer()), to_serde(obj.mask())]
+    if isinstance(obj, NoData):
+        return {NoData.NONE: "None", NoData.DEFAULT: "Default"}.get(obj.kind) or {"Value": _jnum(obj.value())}
+    raise TypeError(type(obj).__name__)
+
+
+def from_serde(kind, data):
+    """Inverse of to_serde for kind in (CellType, CellValue, CellBuffer, Mask, MaskedCellBuffer)."""
+    if kind is CellType:
+        return CellType.from_str(data)
+    if kind is CellValue:
+        ((name, v),) = data.items()
+        return CellValue(CellType.from_str(name), float("nan") if v is None else v)
+    if kind is CellBuffer:
+        ((name, vals),) = data.items()
+        ct = CellType.from_str(name)
+        return CellBuffer.from_vec(np.array([float("nan") if v is None else v for v in vals], dtype=ct.dtype))
+    if kind is Mask:
+        return Mask.new(data)
+    if kind is MaskedCellBuffer:
+        return MaskedCellBuffer(from_serde(CellBuffer, data[0]), from_serde(Mask, data[1]))
+    raise TypeError(kind)
