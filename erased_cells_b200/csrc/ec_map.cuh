@@ -23,7 +23,7 @@ template <class L, class R, int OP> struct BinaryF {  // src/value.rs:199-209
 };
 template <class L> struct ScalarF {  // src/buffer.rs:346-352; rhs is `s as f64`, converted once on the host
     using A = L; using O = double;
-    int op; double s; bool s_fp;
+    int op; double s;
     __device__ __forceinline__ double operator()(L a) const { return f64_op_rt<true, true>(op, as_f64(a), s); }
 };
 template <class T> struct NegF {  // src/value.rs:224-240

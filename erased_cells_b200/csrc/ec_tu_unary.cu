@@ -21,7 +21,7 @@ static cudaError_t go1(const Launch& Lc, const typename F::A* a, typename F::O* 
 
 cudaError_t launch_scalar(const Launch& Lc, int op, int lct, const void* l, double s, double* out, size_t n) {
     switch (lct) {
-#define X(id, p) case id: return go1(Lc, static_cast<const p*>(l), out, n, ScalarF<p>{op, s, true});
+#define X(id, p) case id: return go1(Lc, static_cast<const p*>(l), out, n, ScalarF<p>{op, s});
         EC_WITH_CT(X)
 #undef X
     }

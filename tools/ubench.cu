@@ -122,7 +122,7 @@ template <int VB, int UNROLL, int THREADS> static void sweep(size_t n, void* in0
     run_map2<BinaryF<int16_t, int16_t, OP_SUB>, VB, UNROLL, THREADS>("masked_sub_i16_i16", (const int16_t*)in0, (const int16_t*)in1, o, n, {}, 12.375, m0, m1, m2);
     run_map2<BinaryF<double, double, OP_DIV>, VB, UNROLL, THREADS>("div_f64_f64", (const double*)in0, (const double*)in1, o, n / 2, {}, 24);
     run_map2<NormDiffF<uint16_t, uint16_t>, VB, UNROLL, THREADS>("normdiff_u16", (const uint16_t*)in0, (const uint16_t*)in1, o, n, {}, 12);
-    run_map1<ScalarF<double>, VB, UNROLL, THREADS>("mul_f64_scalar", (const double*)in0, o, n / 2, ScalarF<double>{OP_MUL, 0.5, true}, 16);
+    run_map1<ScalarF<double>, VB, UNROLL, THREADS>("mul_f64_scalar", (const double*)in0, o, n / 2, ScalarF<double>{OP_MUL, 0.5}, 16);
     run_map1<CastF<uint8_t, uint16_t>, VB, UNROLL, THREADS>("cast_u8_u16", (const uint8_t*)in0, (uint16_t*)outp, n, {}, 3);
     run_map1<CastF<uint8_t, double>, VB, UNROLL, THREADS>("cast_u8_f64", (const uint8_t*)in0, o, n, {}, 9);
     run_map1<CastF<uint64_t, double>, VB, UNROLL, THREADS>("cast_u64_f64", (const uint64_t*)in0, o, n / 2, {}, 16);
