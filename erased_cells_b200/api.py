@@ -626,8 +626,14 @@ class MaskedCellBuffer:
         self._mask.put(index, mask)
 
     def extend(self, pairs) -> None:
+        """Extend<(C, bool)> (src/masked/masked_buffer.rs:274-281). Python numbers follow Rust's literal defaults
+        (int -> i32, float -> f64); numpy scalars keep their type."""
         pairs = list(pairs)
-        self._buf.extend(np.array([p[0] for p in pairs], dtype=self.cell_type().dtype if pairs and isinstance(pairs[0][0], (int, float)) else None))
+        if not pairs:
+            return
+        v0 = pairs[0][0]
+        dt = v0.dtype if isinstance(v0, np.generic) else (np.int32 if isinstance(v0, int) else np.float64)
+        self._buf.extend(np.array([p[0] for p in pairs], dtype=dt))
         self._mask.extend([p[1] for p in pairs])
 
     def counts(self):

@@ -184,6 +184,14 @@ def test_get_masked():  # src/masked/masked_buffer.rs:427-440
     assert buf.get_masked(5) is None
 
 
+def test_masked_extend_and_from_iter():  # src/masked/masked_buffer.rs:449-462
+    buf = MaskedCellBuffer.fill(3, CellValue.new(0))
+    buf.extend([(1, False)])
+    assert buf.get_masked(0) == CellValue.new(0) and buf.get_masked(3) is None
+    buf = MaskedCellBuffer.from_vec(np.arange(5, dtype=np.int16))
+    assert buf.mask().all(True) and list(buf.to_vec(CellType.Int16)) == [0, 1, 2, 3, 4]
+
+
 def test_masked_convert():  # src/masked/masked_buffer.rs:442-447
     buf = MaskedCellBuffer.fill_with_mask_via(4, filler_masker, u8)
     r = buf.convert(CellType.Float64)
