@@ -138,7 +138,7 @@ class ClockSampler:
 # =================================================================================================
 # reference arm: the reference's CPU algorithm (oracle port: per-cell tagged dispatch) on host cores
 # =================================================================================================
-def run_reference(args):
+def run_reference(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -176,7 +176,7 @@ def run_reference(args):
     cells = len(pairs) * per_thread * threads
     value = cells * args.steps / dt / 1e9
     sample = f"{len(pairs)} legal pairs x {per_thread} cells x {threads} threads per step (same seeds as the GPU workload)"
-    print(json.dumps({
+    out.emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Gcells/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8..f64 casts (integer/f32/f64)", "data": "synthetic",
@@ -186,7 +186,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "Gcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is Rust (no toolchain in this image): timed the C++ restatement oracle/, faithful per-cell tagged path, "
                 "one independent strip per host thread (the reference itself is single-threaded)",
-    }))
+    })
 
 
 def bind_to_gpu_numa_node(index: int):
@@ -210,7 +210,7 @@ def bind_to_gpu_numa_node(index: int):
 # =================================================================================================
 # this repo's arm
 # =================================================================================================
-def run_ours(args):
+def run_ours(args, out):
     import torch
     import torch.distributed as dist
 
@@ -402,7 +402,7 @@ def run_ours(args):
                          f"(reference is single-threaded), {t:.1f} s of CPU work", "host_cores_available": os.cpu_count()}
 
     if rank == 0:
-        out = {
+        line = {
             "metric": METRIC, "value": value, "unit": "Gcells/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8..f64 casts (integer/f32/f64)", "data": "synthetic",
@@ -415,7 +415,7 @@ def run_ours(args):
             "GBps_algorithmic_step": round(step_bytes * world / (ms_per_step * 1e-3) / 1e9, 1),
             "per_pair": per_pair, "configs": configs,
         }
-        print(json.dumps(out))
+        out.emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -535,6 +535,26 @@ def other_configs(ec, L, torch, dist, rank, world, barrier, max_over_ranks, peak
     return res
 
 
+class OneLineStdout:
+    """The contract is ONE JSON line on stdout. Libraries underneath (NCCL's version banner, for one) write to fd 1
+    on their own, so for the duration of the run fd 1 is pointed at stderr and the line is written to the saved fd."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, obj):
+        os.write(self.saved, (json.dumps(obj) + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -546,10 +566,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-configs", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    with OneLineStdout() as out:
+        if args.impl == "reference":
+            run_reference(args, out)
+        else:
+            run_ours(args, out)
 
 
 if __name__ == "__main__":
