@@ -480,6 +480,12 @@ def other_configs(ec, L, torch, dist, rank, world, barrier, max_over_ranks, peak
     c3["masked_sub_i16_i16"] = entry(timed(lambda: ma - mb), 12.375 * n3, n3)
     r = ma - mb
     c3["masked_mul_scalar_f64"] = entry(timed(lambda: r * 0.0001), 16.0 * n3, n3, note="buffer kernel only; the mask is cloned (1/4 B/cell more)")
+    def c3_lazy():  # `(&ma - &mb) * 0.0001` through the operators, deferred: one fused data pass + the mask AND
+        with ec.lazy():
+            x = (ma - mb) * 0.0001
+            x.buffer().device_ptr()
+        return x
+    c3["masked_sub_then_scale_lazy_1_pass"] = entry(timed(c3_lazy), 12.0 * n3, n3, note="data kernel 12 B/cell; mask AND + clone ride along (5/8 B/cell)")
     rs = r * 0.0001
     c3["masked_min_max_f64"] = entry(timed(lambda: rs.min_max()), 8.125 * n3, n3, note="includes the 16-byte D2H + stream sync of the result")
     c3["counts"] = entry(timed(lambda: rs.counts()), 0.125 * n3, n3)

@@ -459,6 +459,8 @@ cudaError_t launch_normdiff(const Launch& L, int lct, const void* l, int rct, co
 }
 cudaError_t launch_binary_scalar(const Launch& L, int op1, int lct, const void* l, int rct, const void* r, int op2, double s,
                                  double* out, size_t n) {
+    const cudaError_t e = launch_binary_scalar_static(L, op1, lct, l, rct, r, op2, s, out, n);  // compile-time ops where instantiated
+    if (e != cudaErrorNotSupported) return e;
     return kBinScalar[lct](L, op1, l, rct, r, op2, s, out, n);
 }
 

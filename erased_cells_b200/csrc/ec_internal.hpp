@@ -72,6 +72,8 @@ cudaError_t launch_fill_nodata(const Launch& L, int sct, const void* a, const ui
 cudaError_t launch_normdiff(const Launch& L, int lct, const void* l, int rct, const void* r, double* out, size_t n);
 cudaError_t launch_binary_scalar(const Launch& L, int op1, int lct, const void* l, int rct, const void* r, int op2,
                                  double s, double* out, size_t n);
+cudaError_t launch_binary_scalar_static(const Launch& L, int op1, int lct, const void* l, int rct, const void* r, int op2,
+                                        double s, double* out, size_t n);
 // reductions: results land in scratch.result[0..1] (device); keys are unsigned order keys
 cudaError_t launch_min_max(const Launch& L, int ct, const void* a, const uint32_t* mask, size_t n,
                            const ReduceScratch& s);

@@ -54,6 +54,17 @@ template <class L, class R> struct BinaryScalarF {
     }
 };
 
+// the same with both ops known at compile time (one division body at most per op instead of a 4-way switch each):
+// instantiated for same-typed operands and the README's u8/u16 pair (ec_tu_fused.cu), the rest use the runtime form
+template <class L, class R, int OP1, int OP2> struct BinaryScalarT {
+    using A = L; using B = R; using O = double;
+    double s;
+    __device__ __forceinline__ double operator()(L a, R b) const {
+        const double t = f64_op<OP1, is_fp<L>, is_fp<R>>(as_f64(a), as_f64(b));
+        return f64_op<OP2, true, true>(t, s);
+    }
+};
+
 // ---- one-input map -----------------------------------------------------------------------------
 template <class F, int VB, int UNROLL, int THREADS>
 __global__ void __launch_bounds__(THREADS) map1_kernel(const typename F::A* __restrict__ a,
