@@ -382,3 +382,38 @@ def test_lazy_chains_fuse_and_match_eager(orc):
             assert mr.buffer() == eager_ndvi and mr.counts() == (n, 0)
             assert (CellBuffer.from_vec(l[:0]) + a).cell_type() == CellType.UInt8   # empty stays the reference's UInt8([])
         assert not L.ec_get_lazy()
+
+
+def test_concurrent_host_threads(orc):
+    """The C ABI is callable from any thread (SURVEY.md §8b threading): four host threads issue ops, reductions and
+    comparisons at the same time on shared read-only inputs and private outputs; every result is still bit-exact."""
+    import threading
+    n = (1 << 20) + 77
+    a_h, b_h = synth.host(CellType.UInt16, n, 0x7A1), synth.host(CellType.Float32, n, 0x7A2)
+    a, b = CellBuffer.from_vec(a_h), CellBuffer.from_vec(b_h)
+    want = {op: orc.tight_binary(op, a_h, b_h) for op in range(4)}
+    want_mm = orc.tight_min_max(b_h)
+    errors = []
+
+    def worker(tid):
+        try:
+            for it in range(12):
+                op = (tid + it) % 4
+                r = a._bin(op, b)
+                if not np.array_equal(bits(r.to_vec()), bits(want[op])):
+                    errors.append((tid, it, "binary"))
+                mn, mx = b.min_max()
+                if (mn.bits, mx.bits) != (want_mm[0].bits, want_mm[1].bits):
+                    errors.append((tid, it, "min_max"))
+                if not (r == a._bin(op, b)) or r.convert(CellType.Float64).cmp(r) != 0:
+                    errors.append((tid, it, "cmp"))
+                m = MaskedCellBuffer.from_buffer_with_nodata(a, NoData.new(CellType.UInt16, a_h[tid]))
+                if m.counts() != orc.mask_counts(a_h != a_h[tid]):
+                    errors.append((tid, it, "counts"))
+        except Exception as e:  # noqa: BLE001
+            errors.append((tid, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors[:5]
