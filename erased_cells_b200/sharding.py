@@ -106,3 +106,82 @@ class Comm:
         if self._h:
             lib().ec_comm_destroy(self._h)
             self._h = None
+
+
+class ShardedCellBuffer:
+    """One raster, row-strip sharded over the ranks of a Comm: this rank holds `strip` (rows
+    [row0, row0 + rows)). Element-wise ops, neg and convert are shard-local and return another ShardedCellBuffer;
+    min_max finishes across the GPUs (one fused kernel per GPU when the Comm has the peer exchange)."""
+
+    def __init__(self, strip, width: int, height: int, comm: Comm):
+        self.strip, self.width, self.height, self.comm = strip, width, height, comm
+        self.offset, local = row_strip(width, height, comm.n_ranks, comm.rank)
+        assert strip.len() == local, "strip length does not match this rank's row strip"
+
+    @staticmethod
+    def from_host(raster: np.ndarray, comm: Comm) -> "ShardedCellBuffer":
+        """Every rank passes the same (height, width) host raster (or a memmap of it) and uploads only its strip."""
+        h, w = raster.shape
+        off, ln = row_strip(w, h, comm.n_ranks, comm.rank)
+        return ShardedCellBuffer(CellBuffer.from_vec(raster.reshape(-1)[off:off + ln]), w, h, comm)
+
+    def _like(self, strip):
+        return type(self)(strip, self.width, self.height, self.comm)
+
+    def len(self) -> int:
+        return self.width * self.height
+
+    def cell_type(self) -> CellType:
+        return self.strip.cell_type()
+
+    def _bin(self, op, rhs):
+        return self._like(self.strip._bin(op, rhs.strip if isinstance(rhs, ShardedCellBuffer) else rhs))
+
+    def __add__(self, r): return self._bin(0, r)
+    def __sub__(self, r): return self._bin(1, r)
+    def __mul__(self, r): return self._bin(2, r)
+    def __truediv__(self, r): return self._bin(3, r)
+    def __neg__(self): return self._like(-self.strip)
+
+    def convert(self, ct: CellType):
+        return self._like(self.strip.convert(ct))
+
+    def min_max(self):
+        return self.comm.min_max(self.strip)
+
+    def gather(self) -> np.ndarray:
+        """The whole raster on every rank's host (tests / small rasters)."""
+        import torch.distributed as dist
+        parts = [None] * self.comm.n_ranks
+        dist.all_gather_object(parts, self.strip.to_vec())
+        return np.concatenate(parts).reshape(self.height, self.width)
+
+
+class ShardedMaskedCellBuffer:
+    """Row-strip sharded MaskedCellBuffer: ops propagate the strip's mask locally; min_max / counts cross GPUs."""
+
+    def __init__(self, strip, width: int, height: int, comm: Comm):
+        self.strip, self.width, self.height, self.comm = strip, width, height, comm
+
+    @staticmethod
+    def from_host_with_nodata(raster: np.ndarray, nodata, comm: Comm) -> "ShardedMaskedCellBuffer":
+        from .api import MaskedCellBuffer
+        h, w = raster.shape
+        off, ln = row_strip(w, h, comm.n_ranks, comm.rank)
+        buf = CellBuffer.from_vec(raster.reshape(-1)[off:off + ln], wait=False)
+        return ShardedMaskedCellBuffer(MaskedCellBuffer.from_buffer_with_nodata(buf, nodata), w, h, comm)
+
+    def _bin(self, op, rhs):
+        return ShardedMaskedCellBuffer(self.strip._bin(op, rhs.strip if isinstance(rhs, ShardedMaskedCellBuffer) else rhs),
+                                       self.width, self.height, self.comm)
+
+    def __add__(self, r): return self._bin(0, r)
+    def __sub__(self, r): return self._bin(1, r)
+    def __mul__(self, r): return self._bin(2, r)
+    def __truediv__(self, r): return self._bin(3, r)
+
+    def min_max(self):
+        return self.comm.min_max(self.strip.buffer(), self.strip.mask())
+
+    def counts(self):
+        return self.comm.counts(self.strip.mask())

@@ -56,6 +56,28 @@ for ct in (CellType.Float32, CellType.Int16, CellType.UInt8, CellType.Float64, C
     ok &= good
     del whole, strip, ms, mw
 
+# the sharded raster types: NDVI on the Landsat-like fixture layout, every rank uploads only its strip
+rng = np.random.default_rng(7)
+nir_h = rng.integers(5000, 40000, size=(1031, 512), dtype=np.uint16)
+red_h = rng.integers(5000, 40000, size=(1031, 512), dtype=np.uint16)
+nir_h[rng.random(nir_h.shape) < 0.01] = 0
+nir_s, red_s = sharding.ShardedCellBuffer.from_host(nir_h, comm_obj), sharding.ShardedCellBuffer.from_host(red_h, comm_obj)
+with ec.lazy():
+    ndvi = (nir_s - red_s) / (nir_s + red_s)
+one = (CellBuffer.from_vec(nir_h.reshape(-1)) - CellBuffer.from_vec(red_h.reshape(-1))) / (CellBuffer.from_vec(nir_h.reshape(-1)) + CellBuffer.from_vec(red_h.reshape(-1)))
+good = tuple(v.bits for v in ndvi.min_max()) == tuple(v.bits for v in one.min_max())
+good &= np.array_equal(ndvi.gather().reshape(-1).view(np.uint64), one.to_vec().view(np.uint64))
+nd = NoData.new(CellType.UInt16, 0)
+mn_s = sharding.ShardedMaskedCellBuffer.from_host_with_nodata(nir_h, nd, comm_obj)
+mr_s = sharding.ShardedMaskedCellBuffer.from_host_with_nodata(red_h, nd, comm_obj)
+m_ndvi = (mn_s - mr_s) / (mn_s + mr_s)
+m_one = (MaskedCellBuffer.from_vec_with_nodata(nir_h.reshape(-1), nd) - MaskedCellBuffer.from_vec_with_nodata(red_h.reshape(-1), nd))
+m_one = m_one / (MaskedCellBuffer.from_vec_with_nodata(nir_h.reshape(-1), nd) + MaskedCellBuffer.from_vec_with_nodata(red_h.reshape(-1), nd))
+good &= m_ndvi.counts() == m_one.counts() and tuple(v.bits for v in m_ndvi.min_max()) == tuple(v.bits for v in m_one.min_max())
+if rank == 0:
+    print(f"ShardedCellBuffer / ShardedMaskedCellBuffer NDVI (1031 x 512, ragged strips) == single GPU: {good}, counts {m_ndvi.counts()}")
+ok &= good
+
 # latency of the two ways to finish a sharded f32 min_max (device events around 50 calls)
 strip = synth.device(CellType.Float32, ln, 0xEC40, index_offset=off, kind=synth.REAL_RANGE, lo=-1e4, hi=1e4)
 for label, fn in (("torch.distributed NCCL all-reduce", lambda: sharding.min_max_sharded(strip)), ("ec_comm (peer exchange in the kernel)" if comm_obj.peer_exchange else "ec_comm (NCCL)", lambda: comm_obj.min_max(strip))):
