@@ -195,6 +195,11 @@ static void dev_free(void* p) {
     if (it == g_cache.live.end()) return;
     g_cache.free_by_stream[cur_stream()].emplace(it->second, p);
     g_cache.cached_bytes += it->second;
+    // keep the cache from squatting on the device: past half of HBM, hand everything idle back to the driver
+    if (g_cache.cached_bytes > g_ctx.prop.totalGlobalMem / 2) {
+        cudaStreamSynchronize(cur_stream());
+        cache_release_all_locked();
+    }
 }
 struct DevBlock {
     void* p;

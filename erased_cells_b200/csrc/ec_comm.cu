@@ -125,7 +125,15 @@ static PeerExchange next_exchange(ec_comm* c) {
     px.n_ranks = c->n_ranks;
     px.rank = c->rank;
     px.epoch = ++c->epoch;
-    px.spin_limit = 4000000000ull;  // ~2 s of SM clocks: a missing peer turns into an error, not a hang
+    // A peer that never arrives (a rank skipped the collective, or died) must become an error, not a hung GPU:
+    // give up after EC_PEER_WAIT_SECONDS (default 20) of SM clock ticks.
+    static const unsigned long long limit = [] {
+        int khz = 1900000, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+        return static_cast<unsigned long long>(env_int("EC_PEER_WAIT_SECONDS", 20)) * 1000ull * static_cast<unsigned long long>(khz);
+    }();
+    px.spin_limit = limit;
     return px;
 }
 

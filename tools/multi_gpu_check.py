@@ -73,9 +73,10 @@ mr_s = sharding.ShardedMaskedCellBuffer.from_host_with_nodata(red_h, nd, comm_ob
 m_ndvi = (mn_s - mr_s) / (mn_s + mr_s)
 m_one = (MaskedCellBuffer.from_vec_with_nodata(nir_h.reshape(-1), nd) - MaskedCellBuffer.from_vec_with_nodata(red_h.reshape(-1), nd))
 m_one = m_one / (MaskedCellBuffer.from_vec_with_nodata(nir_h.reshape(-1), nd) + MaskedCellBuffer.from_vec_with_nodata(red_h.reshape(-1), nd))
-good &= m_ndvi.counts() == m_one.counts() and tuple(v.bits for v in m_ndvi.min_max()) == tuple(v.bits for v in m_one.min_max())
+sharded_counts = m_ndvi.counts()  # collectives: every rank calls them
+good &= sharded_counts == m_one.counts() and tuple(v.bits for v in m_ndvi.min_max()) == tuple(v.bits for v in m_one.min_max())
 if rank == 0:
-    print(f"ShardedCellBuffer / ShardedMaskedCellBuffer NDVI (1031 x 512, ragged strips) == single GPU: {good}, counts {m_ndvi.counts()}")
+    print(f"ShardedCellBuffer / ShardedMaskedCellBuffer NDVI (1031 x 512, ragged strips) == single GPU: {good}, counts {sharded_counts}")
 ok &= good
 
 # latency of the two ways to finish a sharded f32 min_max (device events around 50 calls)
