@@ -142,6 +142,13 @@ inline CellValue max_value(CellType ct) { CellValue o; detail::check(ec_ctype_ma
 
 // Defer buffer arithmetic on this thread so op chains fuse into single passes over HBM (bit-identical results).
 inline void set_lazy(bool on) { detail::check(ec_set_lazy(on ? 1 : 0)); }
+struct LazyScope {  // RAII: `{ LazyScope lazy; auto ndvi = (nir - red) / (nir + red); ... }`
+    int prev;
+    LazyScope() : prev(ec_get_lazy()) { set_lazy(true); }
+    ~LazyScope() { ec_set_lazy(prev); }
+    LazyScope(const LazyScope&) = delete;
+    LazyScope& operator=(const LazyScope&) = delete;
+};
 
 // ---- CellBuffer — src/buffer.rs; BufferOps — src/lib.rs:104-163 -----------------------------------------------
 class Mask;
@@ -198,6 +205,11 @@ public:
     static CellBuffer scalar(int op, const CellBuffer& l, const CellValue& r) { ec_buf* h; detail::check(ec_buf_scalar(op, l.h_, &r.v, &h)); return own(h); }
     CellBuffer operator-() const { ec_buf* h; detail::check(ec_buf_neg(h_, &h)); return own(h); }
     CellBuffer normalized_difference(const CellBuffer& o) const { ec_buf* h; detail::check(ec_buf_normalized_difference(h_, o.h_, &h)); return own(h); }
+    CellBuffer binary_scalar(int op1, const CellBuffer& o, int op2, const CellValue& s) const {
+        ec_buf* h;
+        detail::check(ec_buf_binary_scalar(op1, h_, o.h_, op2, &s.v, &h));
+        return own(h);
+    }
     std::string debug() const {  // src/buffer.rs:188-203 + Elided
         const std::vector<double> v = convert(CellType::Float64).to_vec<double>();
         std::string s = to_string(cell_type()) + "CellBuffer(";

@@ -229,9 +229,31 @@ static void masked_tests() {
     }
 }
 
+// not in the reference: the same operator chains deferred and fused must give the same buffers
+static void lazy_tests() {
+    std::vector<uint16_t> nir(5000), red(5000);
+    for (size_t i = 0; i < nir.size(); ++i) { nir[i] = uint16_t(5000 + (i * 7919) % 30000); red[i] = uint16_t(i % 17 == 0 ? nir[i] : 5000 + (i * 104729) % 30000); }
+    nir[3] = red[3] = 0;  // 0/0
+    const CellBuffer n = CellBuffer::from_vec(nir), r = CellBuffer::from_vec(red);
+    const CellBuffer eager = (n - r) / (n + r);
+    const CellBuffer eager_chain = n / r * 0.5;
+    const uint64_t before = ec_kernel_launches();
+    {
+        LazyScope lazy;
+        CellBuffer ndvi = (n - r) / (n + r);
+        CellBuffer chain = n / r * 0.5;
+        CHECK(ec_kernel_launches() == before);            // nothing ran yet
+        CHECK(ndvi == eager);                             // one fused kernel + the comparison
+        CHECK(chain == eager_chain);
+        CHECK(ndvi == n.normalized_difference(r));
+        CHECK(chain == n.binary_scalar(EC_DIV, r, EC_MUL, CellValue(0.5)));
+    }
+    CHECK(ec_get_lazy() == 0);
+}
+
 int main() {
     try {
-        can_union(); ctype_misc(); value_tests(); buffer_tests(); mask_tests(); nodata_tests(); masked_tests();
+        can_union(); ctype_misc(); value_tests(); buffer_tests(); mask_tests(); nodata_tests(); masked_tests(); lazy_tests();
     } catch (const std::exception& e) {
         std::fprintf(stderr, "exception: %s\n", e.what());
         return 2;
