@@ -18,7 +18,17 @@ def test_cpp_reference_port():
     assert " 0 failed" in r.stdout
 
 
+@pytest.mark.gpu
+def test_plain_c_abi_smoke():
+    exe = os.path.join(ROOT, "tests", "cpp", "build", "abi_smoke_c")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "-s"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "c abi ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_cpp_port_builds_on_cpu():
     """the host mirror compiles and links against the C ABI without a GPU"""
     subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "-s"], check=True)
     assert os.path.exists(os.path.join(ROOT, "tests", "cpp", "build", "test_reference_port"))
+    assert os.path.exists(os.path.join(ROOT, "tests", "cpp", "build", "abi_smoke_c"))  # the header is valid C99 (-pedantic -Werror)
