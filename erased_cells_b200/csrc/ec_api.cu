@@ -17,6 +17,7 @@
 
 #include "ec_internal.hpp"
 #include "ec_reduce.cuh"
+#include "ec_vm.cuh"
 
 namespace ec {
 
@@ -508,6 +509,87 @@ static bool same_operand(const Operand& a, const Operand& b) {
     return a.ptr == b.ptr && a.ct == b.ct && a.len == b.len;
 }
 static ec_status eval(Expr& e);
+static ec_status eval_operand(Operand& o);
+
+// ---- compiling a pending tree into one VmProgram (ec_vm.cuh) -------------------------------------------
+// A child is inlined when nothing else can ask for its value: it is pending and this parent holds the only
+// reference. Anything shared (the user kept the handle, or two parents use it) is evaluated once and becomes an
+// input. Code generation leaves each subtree's value in the accumulator; when both sides are subtrees the first
+// one is parked in a temporary (3 available). Running out of inputs / temporaries / code space is not an error:
+// the caller falls back to evaluating the children separately.
+struct VmBuild {
+    VmProgram p{};
+    int n_const = 0, temps = 0;
+    bool ok = true;
+};
+static bool inlineable(const Operand& o) { return o.expr && !o.expr->done && o.expr.use_count() == 1; }
+static int vm_input(VmBuild& b, const Operand& o) {
+    for (int k = 0; k < b.p.n_in; ++k)
+        if (b.p.in[k] == o.ptr && b.p.ct[k] == o.ct) return k;
+    if (b.p.n_in == kVmInputs) { b.ok = false; return 0; }
+    b.p.in[b.p.n_in] = o.ptr;
+    b.p.ct[b.p.n_in] = o.ct;
+    return b.p.n_in++;
+}
+static int vm_const(VmBuild& b, double c) {
+    uint64_t cb;
+    memcpy(&cb, &c, 8);
+    for (int k = 0; k < b.n_const; ++k) {
+        uint64_t kb;
+        memcpy(&kb, &b.p.consts[k], 8);
+        if (kb == cb) return 8 + k;
+    }
+    if (b.n_const == kVmConsts) { b.ok = false; return 8; }
+    b.p.consts[b.n_const] = c;
+    return 8 + b.n_const++;
+}
+static void vm_emit(VmBuild& b, uint8_t kind, int op, int src) {
+    if (b.p.n_code == kVmCode) { b.ok = false; return; }
+    b.p.code[b.p.n_code++] = VmInstr{kind, static_cast<uint8_t>(op), static_cast<uint8_t>(src), 0};
+}
+static void vm_gen(VmBuild& b, Expr& e);
+static void vm_value(VmBuild& b, Operand& o) {  // o's value -> accumulator
+    if (inlineable(o)) vm_gen(b, *o.expr);
+    else vm_emit(b, VM_LOAD, 0, vm_input(b, o));
+}
+static void vm_gen(VmBuild& b, Expr& e) {
+    if (!b.ok) return;
+    if (e.kind == EX_SCALAR) {
+        vm_value(b, e.l);
+        vm_emit(b, VM_OP, e.op, vm_const(b, e.s));
+    } else if (!inlineable(e.r)) {
+        vm_value(b, e.l);
+        vm_emit(b, VM_OP, e.op, vm_input(b, e.r));
+    } else if (!inlineable(e.l)) {
+        vm_gen(b, *e.r.expr);
+        vm_emit(b, VM_OPR, e.op, vm_input(b, e.l));  // acc = l op acc
+    } else {
+        vm_gen(b, *e.l.expr);
+        if (b.temps == kVmTemps) { b.ok = false; return; }
+        const int t = 4 + b.temps++;
+        vm_emit(b, VM_STORE, 0, t);
+        vm_gen(b, *e.r.expr);
+        vm_emit(b, VM_OPR, e.op, t);
+        --b.temps;
+    }
+}
+// materialise every operand in the tree that cannot be inlined (shared or already-started work)
+static ec_status vm_prepare(Expr& e) {
+    Operand* ops[2] = {&e.l, e.kind == EX_BIN ? &e.r : nullptr};
+    for (Operand* o : ops) {
+        if (!o) continue;
+        if (inlineable(*o)) { if (ec_status s = vm_prepare(*o->expr)) return s; }
+        else if (o->expr) { if (ec_status s = eval_operand(*o)) return s; }
+    }
+    return EC_OK;
+}
+static int vm_ops(const Expr& e) {  // number of ops the tree would fuse
+    int n = 1;
+    if (inlineable(e.l)) n += vm_ops(*e.l.expr);
+    if (e.kind == EX_BIN && inlineable(e.r)) n += vm_ops(*e.r.expr);
+    return n;
+}
+
 static ec_status eval_operand(Operand& o) {
     if (!o.expr) return EC_OK;
     if (ec_status s = eval(*o.expr)) return s;
@@ -535,6 +617,15 @@ static ec_status eval(Expr& e) {
         if (ec_status s = eval_operand(cl->r)) return s;
         err = launch_normdiff(launch_ctx(), cl->l.ct, cl->l.ptr, cl->r.ct, cl->r.ptr, static_cast<double*>(out), e.n);
         family = "normalized_difference(lazy)";
+    } else if (vm_ops(e) >= 2 && [&] {  // a longer chain: one interpreted pass instead of one pass per op
+                   if (vm_prepare(e) != EC_OK) return false;
+                   VmBuild b;
+                   vm_gen(b, e);
+                   if (!b.ok) return false;
+                   err = launch_vm(launch_ctx(), b.p, static_cast<double*>(out), e.n);
+                   family = "expression_vm(lazy)";
+                   return true;
+               }()) {
     } else {
         if (ec_status s = eval_operand(e.l)) return s;
         if (e.kind == EX_BIN) {

@@ -3,6 +3,7 @@
 // run the runtime-op functor of ec_tu_binary.cu (same results, ~1.4x the instructions).
 #include "ec_internal.hpp"
 #include "ec_map.cuh"
+#include "ec_vm.cuh"
 
 #ifndef EC_VB
 #define EC_VB 32
@@ -52,6 +53,12 @@ cudaError_t launch_binary_scalar_static(const Launch& Lc, int op1, int lct, cons
 #undef X
     }
     return cudaErrorNotSupported;
+}
+
+cudaError_t launch_vm(const Launch& Lc, const VmProgram& p, double* out, size_t n) {
+    constexpr size_t TILE = size_t(kThreads) * 4;
+    vm_kernel<kThreads><<<grid_for(n, TILE, Lc), kThreads, 0, Lc.stream>>>(p, out, n);
+    return cudaGetLastError();
 }
 
 }  // namespace ec
