@@ -538,6 +538,26 @@ def other_configs(ec, L, torch, dist, rank, world, barrier, max_over_ranks, peak
     res["c5_ndvi_u16_32768_per_gpu_tile"]["lazy_operators_1_pass"] = entry(timed(c5_lazy, 3, 1), 12.0 * n5, n5)
     nd5 = nir.normalized_difference(red)
     res["c5_ndvi_u16_32768_per_gpu_tile"]["min_max_f64"] = entry(timed(lambda: nd5.min_max(), 3, 1), 8.0 * n5, n5)
+
+    # beyond the BASELINE configs: a longer band-math chain through the operators, EVI = 2.5*(nir-red)/(nir+6*red-7.5*blue+1),
+    # 8 ops over three u16 bands — op by op vs. one interpreted pass (expression VM) in lazy mode
+    del nir, red, nd5
+    ne = 16384 * 16384
+    b_nir, b_red, b_blue = [synth.device(CellType.UInt16, ne, 0xEC60 + i, kind=synth.INT_RANGE, lo=100, hi=40000) for i in range(3)]
+
+    def evi():
+        return ((b_nir - b_red) * 2.5) / (((b_nir + b_red * 6.0) - b_blue * 7.5) + 1.0)
+
+    def evi_lazy():
+        with ec.lazy(vm=True):
+            r = evi()
+            r.device_ptr()
+        return r
+    unfused_bytes = (2 + 2 + 8) + 16 + (2 + 8) + (2 + 8 + 8) + (2 + 8) + 24 + 16 + 24  # per cell, op by op
+    res["extra_evi_u16_16384"] = {"unfused_8_ops": entry(timed(evi, 3, 1), float(unfused_bytes) * ne, ne),
+                                  "lazy_expression_vm_1_pass": entry(timed(evi_lazy, 3, 1), 14.0 * ne, ne),
+                                  "note": "not a BASELINE config; the expression VM is opt-in (ec_set_lazy(2)): interpretation overhead eats the traffic it saves; "
+                                          "GB/s of the VM line = 14 B/cell (3 x u16 in, f64 out) / time"}
     return res
 
 

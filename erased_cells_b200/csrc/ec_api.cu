@@ -479,7 +479,7 @@ cudaError_t launch_binary_scalar(const Launch& L, int op1, int lct, const void* 
 //     (X op1 Y) op2 scalar   -> one binary-then-scalar kernel      (27 -> 11 B/cell for u8/u16*0.5)
 // Every op keeps its own IEEE rounding, so results are bit-identical to eager evaluation. Operands are
 // immutable snapshots: put/extend on a buffer that a pending Expr still references copy it first.
-static thread_local bool t_lazy = false;
+static thread_local int t_lazy = 0;  // 0 eager, 1 deferred with the dedicated fused shapes, 2 also the expression VM
 enum : int { EX_BIN = 0, EX_SCALAR = 1 };
 struct Operand {
     uint8_t ct = 0;
@@ -545,7 +545,7 @@ static int vm_const(VmBuild& b, double c) {
 }
 static void vm_emit(VmBuild& b, uint8_t kind, int op, int src) {
     if (b.p.n_code == kVmCode) { b.ok = false; return; }
-    b.p.code[b.p.n_code++] = VmInstr{kind, static_cast<uint8_t>(op), static_cast<uint8_t>(src), 0};
+    b.p.code[b.p.n_code++] = vm_word(kind, op, src);
 }
 static void vm_gen(VmBuild& b, Expr& e);
 static void vm_value(VmBuild& b, Operand& o) {  // o's value -> accumulator
@@ -567,7 +567,7 @@ static void vm_gen(VmBuild& b, Expr& e) {
         vm_gen(b, *e.l.expr);
         if (b.temps == kVmTemps) { b.ok = false; return; }
         const int t = 4 + b.temps++;
-        vm_emit(b, VM_STORE, 0, t);
+        vm_emit(b, VM_STORE, t - 4, 7);
         vm_gen(b, *e.r.expr);
         vm_emit(b, VM_OPR, e.op, t);
         --b.temps;
@@ -617,7 +617,7 @@ static ec_status eval(Expr& e) {
         if (ec_status s = eval_operand(cl->r)) return s;
         err = launch_normdiff(launch_ctx(), cl->l.ct, cl->l.ptr, cl->r.ct, cl->r.ptr, static_cast<double*>(out), e.n);
         family = "normalized_difference(lazy)";
-    } else if (vm_ops(e) >= 2 && [&] {  // a longer chain: one interpreted pass instead of one pass per op
+    } else if (t_lazy >= 2 && vm_ops(e) >= 2 && [&] {  // opt-in: a longer chain as one interpreted pass (ec_vm.cuh)
                    if (vm_prepare(e) != EC_OK) return false;
                    VmBuild b;
                    vm_gen(b, e);
@@ -784,11 +784,12 @@ size_t ec_cached_bytes(void) {
     return g_cache.cached_bytes;
 }
 uint64_t ec_guard_violations(void) { return g_guard_violations.load(); }
-ec_status ec_set_lazy(int on) {
-    t_lazy = on != 0;
+ec_status ec_set_lazy(int mode) {
+    if (mode < 0 || mode > 2) return invalid("lazy mode");
+    t_lazy = mode;
     return EC_OK;
 }
-int ec_get_lazy(void) { return t_lazy ? 1 : 0; }
+int ec_get_lazy(void) { return t_lazy; }
 uint64_t ec_kernel_launches(void) { return g_launches.load(); }
 const char* ec_last_kernel(void) { return t_last_kernel; }
 ec_status ec_event_create(ec_event** out) {

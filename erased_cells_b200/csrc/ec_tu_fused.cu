@@ -56,7 +56,7 @@ cudaError_t launch_binary_scalar_static(const Launch& Lc, int op1, int lct, cons
 }
 
 cudaError_t launch_vm(const Launch& Lc, const VmProgram& p, double* out, size_t n) {
-    constexpr size_t TILE = size_t(kThreads) * 4;
+    constexpr size_t TILE = size_t(kThreads) * EC_VM_V;
     vm_kernel<kThreads><<<grid_for(n, TILE, Lc), kThreads, 0, Lc.stream>>>(p, out, n);
     return cudaGetLastError();
 }

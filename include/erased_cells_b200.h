@@ -190,8 +190,10 @@ ec_status ec_buf_cmp(const ec_buf* l, const ec_buf* r, int* ordering);
  * ec_set_lazy(1) (per thread, default 0): ec_buf_binary / ec_buf_scalar / ec_masked_binary return at once with a
  * pending result over refcounted snapshots of their operands; the first access evaluates it, fusing
  * `(X - Y) / (X + Y)` and `(X op1 Y) op2 scalar` into one pass over HBM. Results are bit-identical to eager
- * evaluation; later put/extend on an operand do not affect a pending result (copy on write). */
-ec_status ec_set_lazy(int on);
+ * evaluation; later put/extend on an operand do not affect a pending result (copy on write).
+ * ec_set_lazy(2) additionally sends longer chains through the expression VM (one interpreted pass, ec_vm.cuh) —
+ * experimental: bit-identical, but measured only 1.1x faster than op-by-op evaluation on an 8-op chain. */
+ec_status ec_set_lazy(int mode);
 int ec_get_lazy(void);
 /* `(&a - &b) / (&a + &b)` with the three roundings of the unfused chain; 1 pass over HBM */
 ec_status ec_buf_normalized_difference(const ec_buf* a, const ec_buf* b, ec_buf** out);

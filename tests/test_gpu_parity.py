@@ -433,7 +433,7 @@ def test_lazy_expression_vm_matches_eager(orc):
     # EVI = 2.5 * (nir - red) / (nir + 6 * red - 7.5 * blue + 1): 8 ops, 3 inputs, one launch
     nir, red, blue = dev[1], dev[1 + 1], dev[0]
     eager = ((nir - red) * 2.5) / (((nir + red * 6.0) - blue * 7.5) + 1.0)
-    with ec.lazy():
+    with ec.lazy(vm=True):
         k0 = L.ec_kernel_launches()
         evi = ((nir - red) * 2.5) / (((nir + red * 6.0) - blue * 7.5) + 1.0)
         got = evi.to_vec()
@@ -463,18 +463,19 @@ def test_lazy_expression_vm_matches_eager(orc):
         leaves = int(rng.integers(1, 7))
         f = build(int(rng.integers(2, 6)), leaves)
         e = f(dev)
-        with ec.lazy():
-            lz = f(dev)
-            assert lz == e, trial                      # device-side bitwise comparison forces the evaluation
+        for vm in (True, False):
+            with ec.lazy(vm=vm):
+                lz = f(dev)
+                assert lz == e, (trial, vm)            # device-side bitwise comparison forces the evaluation
     # shared sub-expression: evaluated once, used by two parents and by the user
-    with ec.lazy():
+    with ec.lazy(vm=True):
         num = dev[1] - dev[2]
         a = (num * 2.0 + dev[0]) / (num - 1.0)
         b = num / 3.0
         ea = ((dev[1] - dev[2]) * 2.0 + dev[0]) / ((dev[1] - dev[2]) - 1.0)
     assert a == ea and b == (dev[1] - dev[2]) / 3.0 and num == dev[1] - dev[2]
     # a chain far longer than the VM's code space falls back (still right, just more launches)
-    with ec.lazy():
+    with ec.lazy(vm=True):
         x = dev[3]
         for i in range(60):
             x = x * 1.0001 + dev[4]
