@@ -1,102 +1,405 @@
-//! Replaced bodies of `src/buffer.rs` and `src/masked/*` over the C ABI (SOURCE ONLY, never compiled here).
-//! The public names (`CellBuffer`, `BufferOps`, `Mask`, `MaskedCellBuffer`, the std::ops impls) are unchanged;
-//! what changes is the backing store: an owning device handle instead of `Vec<$p>`.
+//! Replaced bodies of `src/buffer.rs` and `src/masked/*` over the C ABI.
+//!
+//! SOURCE ONLY — this image has no Rust toolchain, so this file has never been compiled; it is written to be
+//! dropped into the crate next to `ffi.rs`. The public names (`CellBuffer`, `BufferOps`,
+//! `Mask`, `MaskedCellBuffer`, `NoData`, the std::ops impls) are unchanged; what changes is the backing store:
+//! an owning device handle instead of `Vec<$p>`. The same calls, compiled and tested, live in
+//! `include/erased_cells.hpp` (C++) and `erased_cells_b200/api.py` (Python).
 use crate::error::{Error, Result};
 use crate::ffi::*;
-use crate::{BufferOps, CellEncoding, CellType, CellValue};
+use crate::{with_ct, BufferOps, CellEncoding, CellType, CellValue, NoData};
+use std::cmp::Ordering;
+use std::ops::{Add, BitAnd, BitOr, Div, Mul, Neg, Not, Sub};
 use std::ptr;
 
-fn ct(v: u8) -> CellType { CellType::iter().nth(v as usize).unwrap() }
+// ---- plumbing ------------------------------------------------------------------------------------------
+fn ct(v: u8) -> CellType {
+    CellType::iter().nth(v as usize).expect("cell type discriminant")
+}
 fn check(s: ec_status) -> Result<()> {
     match s {
         EC_OK => Ok(()),
         EC_NARROWING => {
             let (mut a, mut b) = (0u8, 0u8);
             unsafe { ec_last_narrowing(&mut a, &mut b) };
-            Err(Error::NarrowingError { src: ct(a), dst: ct(b) })          // src/error.rs:14-15
+            Err(Error::NarrowingError { src: ct(a), dst: ct(b) }) // src/error.rs:14-15
         }
-        EC_OOB => panic!("index out of bounds"),                             // src/lib.rs:136-147
-        EC_LEN_MISMATCH => panic!("Mask and buffer must have the same length."), // src/masked/masked_buffer.rs:49-53
+        EC_OOB => panic!("index out of bounds"),                                   // src/lib.rs:136-147
+        EC_LEN_MISMATCH => panic!("Mask and buffer must have the same length."),   // src/masked/masked_buffer.rs:49-53
         _ => panic!("erased_cells_b200: {}", unsafe { std::ffi::CStr::from_ptr(ec_last_error()) }.to_string_lossy()),
     }
 }
-fn to_ffi(v: CellValue) -> ec_value { /* tag + little-endian payload, with_ct! match */ unimplemented!() }
-fn from_ffi(v: ec_value) -> CellValue { /* inverse */ unimplemented!() }
+/// `CellValue` <-> the 16-byte `ec_value` (tag + little-endian payload in the low bytes).
+fn to_ffi(v: CellValue) -> ec_value {
+    let mut out = ec_value { ct: v.cell_type() as u8, pad: [0; 7], bits: 0 };
+    macro_rules! put {
+        ($( ($id:ident, $p:ident) ),*) => {
+            match v { $( CellValue::$id(x) => {
+                let b = x.to_le_bytes();
+                let mut w = [0u8; 8];
+                w[..b.len()].copy_from_slice(&b);
+                out.bits = u64::from_le_bytes(w);
+            } )* }
+        };
+    }
+    with_ct!(put);
+    out
+}
+fn from_ffi(v: ec_value) -> CellValue {
+    let w = v.bits.to_le_bytes();
+    macro_rules! get {
+        ($( ($id:ident, $p:ident) ),*) => {
+            match ct(v.ct) { $( CellType::$id => {
+                let mut b = [0u8; std::mem::size_of::<$p>()];
+                b.copy_from_slice(&w[..std::mem::size_of::<$p>()]);
+                CellValue::$id(<$p>::from_le_bytes(b))
+            } )* }
+        };
+    }
+    with_ct!(get)
+}
+fn ordering(r: i32) -> Ordering {
+    r.cmp(&0)
+}
 
-/// Was: `pub enum CellBuffer { UInt8(Vec<u8>), ... }` (src/buffer.rs:52). The cell type now lives in the
-/// handle; `cell_type()` asks it. Send + Sync: kernels only read inputs.
+// ---- CellBuffer — was `pub enum CellBuffer { UInt8(Vec<u8>), ... }` (src/buffer.rs:52) ----------------------
+/// The cell type now lives in the handle. Send + Sync: kernels only read their inputs.
 pub struct CellBuffer(*mut ec_buf);
 unsafe impl Send for CellBuffer {}
 unsafe impl Sync for CellBuffer {}
-impl Drop for CellBuffer { fn drop(&mut self) { unsafe { ec_buf_free(self.0) } } }
+impl Drop for CellBuffer {
+    fn drop(&mut self) {
+        unsafe { ec_buf_free(self.0) }
+    }
+}
 impl Clone for CellBuffer {
-    fn clone(&self) -> Self { let mut h = ptr::null_mut(); check(unsafe { ec_buf_clone(self.0, &mut h) }).unwrap(); Self(h) }
+    fn clone(&self) -> Self {
+        let mut h = ptr::null_mut();
+        check(unsafe { ec_buf_clone(self.0, &mut h) }).unwrap();
+        Self(h)
+    }
+}
+impl CellBuffer {
+    pub fn new<T: CellEncoding>(data: Vec<T>) -> Self {
+        Self::from_vec(data)
+    }
 }
 
 impl BufferOps for CellBuffer {
-    fn from_vec<T: CellEncoding>(data: Vec<T>) -> Self {                     // src/buffer.rs:64-66
+    fn from_vec<T: CellEncoding>(data: Vec<T>) -> Self {
+        // src/buffer.rs:64-66. `data` is owned, so the copy could also be left in flight with
+        // ec_buf_from_host_async and the Vec parked in the handle until ec_buf_wait.
         let mut h = ptr::null_mut();
         check(unsafe { ec_buf_from_host(T::cell_type() as u8, data.as_ptr().cast(), data.len(), &mut h) }).unwrap();
-        check(unsafe { ec_synchronize() }).unwrap();                         // `data` is dropped on return
+        check(unsafe { ec_synchronize() }).unwrap();
         Self(h)
     }
-    fn with_defaults(len: usize, c: CellType) -> Self { let mut h = ptr::null_mut(); check(unsafe { ec_buf_with_defaults(len, c as u8, &mut h) }).unwrap(); Self(h) }
-    fn fill(len: usize, value: CellValue) -> Self { let mut h = ptr::null_mut(); check(unsafe { ec_buf_fill(len, &to_ffi(value), &mut h) }).unwrap(); Self(h) }
-    fn fill_via<T: CellEncoding, F: Fn(usize) -> T>(len: usize, f: F) -> Self { Self::from_vec((0..len).map(f).collect()) }
-    fn len(&self) -> usize { unsafe { ec_buf_len(self.0) } }
-    fn cell_type(&self) -> CellType { ct(unsafe { ec_buf_ctype(self.0) }) }
-    fn get(&self, index: usize) -> CellValue { let mut v = unsafe { std::mem::zeroed() }; check(unsafe { ec_buf_get(self.0, index, &mut v) }).unwrap(); from_ffi(v) }
-    fn put(&mut self, index: usize, value: CellValue) -> Result<()> { check(unsafe { ec_buf_put(self.0, index, &to_ffi(value)) }) }
-    fn convert(&self, c: CellType) -> Result<Self> { let mut h = ptr::null_mut(); check(unsafe { ec_buf_convert(self.0, c as u8, &mut h) })?; Ok(Self(h)) }
+    fn with_defaults(len: usize, c: CellType) -> Self {
+        let mut h = ptr::null_mut();
+        check(unsafe { ec_buf_with_defaults(len, c as u8, &mut h) }).unwrap();
+        Self(h)
+    }
+    fn fill(len: usize, value: CellValue) -> Self {
+        let mut h = ptr::null_mut();
+        check(unsafe { ec_buf_fill(len, &to_ffi(value), &mut h) }).unwrap();
+        Self(h)
+    }
+    fn fill_via<T: CellEncoding, F: Fn(usize) -> T>(len: usize, f: F) -> Self {
+        Self::from_vec((0..len).map(f).collect()) // the closure is host code in the reference too
+    }
+    fn len(&self) -> usize {
+        unsafe { ec_buf_len(self.0) }
+    }
+    fn cell_type(&self) -> CellType {
+        ct(unsafe { ec_buf_ctype(self.0) })
+    }
+    fn get(&self, index: usize) -> CellValue {
+        let mut v = ec_value { ct: 0, pad: [0; 7], bits: 0 };
+        check(unsafe { ec_buf_get(self.0, index, &mut v) }).unwrap();
+        from_ffi(v)
+    }
+    fn put(&mut self, index: usize, value: CellValue) -> Result<()> {
+        check(unsafe { ec_buf_put(self.0, index, &to_ffi(value)) })
+    }
+    fn convert(&self, c: CellType) -> Result<Self> {
+        let mut h = ptr::null_mut();
+        check(unsafe { ec_buf_convert(self.0, c as u8, &mut h) })?;
+        Ok(Self(h))
+    }
     fn min_max(&self) -> (CellValue, CellValue) {
-        let (mut a, mut b) = unsafe { (std::mem::zeroed(), std::mem::zeroed()) };
+        let (mut a, mut b) = (ec_value { ct: 0, pad: [0; 7], bits: 0 }, ec_value { ct: 0, pad: [0; 7], bits: 0 });
         check(unsafe { ec_buf_min_max(self.0, ptr::null(), &mut a, &mut b) }).unwrap();
         (from_ffi(a), from_ffi(b))
     }
-    fn to_vec<T: CellEncoding>(self) -> Result<Vec<T>> {                      // src/buffer.rs:175-185
+    fn to_vec<T: CellEncoding>(self) -> Result<Vec<T>> {
+        // src/buffer.rs:175-185: convert on the device, one D2H copy
         let r = self.convert(T::cell_type())?;
-        let mut out = Vec::<T>::with_capacity(r.len());
-        check(unsafe { ec_buf_to_host(r.0, out.as_mut_ptr().cast(), r.len() * std::mem::size_of::<T>()) })?;
-        unsafe { out.set_len(r.len()) };
+        let n = if r.cell_type() == T::cell_type() { r.len() } else { 0 }; // empty non-identity convert is UInt8([])
+        let mut out = Vec::<T>::with_capacity(n);
+        check(unsafe { ec_buf_to_host(r.0, out.as_mut_ptr().cast(), n * std::mem::size_of::<T>()) })?;
+        unsafe { out.set_len(n) };
         Ok(out)
     }
 }
+impl<T: CellEncoding> From<Vec<T>> for CellBuffer {
+    fn from(values: Vec<T>) -> Self {
+        Self::from_vec(values)
+    }
+}
+impl<C: CellEncoding> Extend<C> for CellBuffer {
+    fn extend<I: IntoIterator<Item = C>>(&mut self, iter: I) {
+        // src/buffer.rs:205-221: value-checked `to_<p>().unwrap()` runs on the device; EC_NARROWING is that unwrap's panic
+        let v: Vec<C> = iter.into_iter().collect();
+        check(unsafe { ec_buf_extend_host(self.0, C::cell_type() as u8, v.as_ptr().cast(), v.len()) }).expect("Extend: value out of range");
+    }
+}
 
-macro_rules! cb_bin_op {                                                      // src/buffer.rs:321-358
+macro_rules! cb_bin_op {
+    // src/buffer.rs:321-358
     ($trt:ident, $mth:ident, $code:expr) => {
-        impl std::ops::$trt for &CellBuffer {
+        impl $trt for &CellBuffer {
             type Output = CellBuffer;
-            fn $mth(self, rhs: Self) -> CellBuffer { let mut h = ptr::null_mut(); check(unsafe { ec_buf_binary($code, self.0, rhs.0, &mut h) }).unwrap(); CellBuffer(h) }
+            fn $mth(self, rhs: Self) -> CellBuffer {
+                let mut h = ptr::null_mut();
+                check(unsafe { ec_buf_binary($code, self.0, rhs.0, &mut h) }).unwrap(); // arithmetic never errors
+                CellBuffer(h)
+            }
         }
-        impl std::ops::$trt for CellBuffer { type Output = CellBuffer; fn $mth(self, rhs: Self) -> CellBuffer { std::ops::$trt::$mth(&self, &rhs) } }
-        impl std::ops::$trt<&CellBuffer> for CellBuffer { type Output = CellBuffer; fn $mth(self, rhs: &CellBuffer) -> CellBuffer { std::ops::$trt::$mth(&self, rhs) } }
-        impl<R: Into<CellValue>> std::ops::$trt<R> for CellBuffer {
+        impl $trt for CellBuffer {
             type Output = CellBuffer;
-            fn $mth(self, rhs: R) -> CellBuffer { let mut h = ptr::null_mut(); check(unsafe { ec_buf_scalar($code, self.0, &to_ffi(rhs.into()), &mut h) }).unwrap(); CellBuffer(h) }
+            fn $mth(self, rhs: Self) -> CellBuffer {
+                $trt::$mth(&self, &rhs)
+            }
+        }
+        impl $trt<&CellBuffer> for CellBuffer {
+            type Output = CellBuffer;
+            fn $mth(self, rhs: &CellBuffer) -> CellBuffer {
+                $trt::$mth(&self, rhs)
+            }
+        }
+        impl<R: Into<CellValue>> $trt<R> for CellBuffer {
+            type Output = CellBuffer;
+            fn $mth(self, rhs: R) -> CellBuffer {
+                let mut h = ptr::null_mut();
+                check(unsafe { ec_buf_scalar($code, self.0, &to_ffi(rhs.into()), &mut h) }).unwrap();
+                CellBuffer(h)
+            }
         }
     };
 }
-cb_bin_op!(Add, add, 0); cb_bin_op!(Sub, sub, 1); cb_bin_op!(Mul, mul, 2); cb_bin_op!(Div, div, 3);
-impl std::ops::Neg for &CellBuffer { type Output = CellBuffer; fn neg(self) -> CellBuffer { let mut h = ptr::null_mut(); check(unsafe { ec_buf_neg(self.0, &mut h) }).unwrap(); CellBuffer(h) } }
-impl Ord for CellBuffer { fn cmp(&self, o: &Self) -> std::cmp::Ordering { let mut r = 0; check(unsafe { ec_buf_cmp(self.0, o.0, &mut r) }).unwrap(); r.cmp(&0) } }
-// PartialOrd / PartialEq / Eq delegate to `cmp` as in src/buffer.rs:373-388.
-
-/// Was `Mask(Vec<bool>)` (src/masked/mask.rs:12): packed bits on the device. `Index/IndexMut -> &bool` and
-/// `iter_mut` cannot point into packed device bits; they are served from a host mirror filled by
-/// `ec_mask_to_bools` and written back with `ec_mask_from_bools` on drop of the guard.
-pub struct Mask(*mut ec_mask);
-impl Drop for Mask { fn drop(&mut self) { unsafe { ec_mask_free(self.0) } } }
-impl std::ops::BitAnd for &Mask { type Output = Mask; fn bitand(self, r: Self) -> Mask { let mut h = ptr::null_mut(); check(unsafe { ec_mask_and(self.0, r.0, &mut h) }).unwrap(); Mask(h) } }
-// Not / BitOr / counts / all / fill / get / put map 1:1 onto ec_mask_not / _or / _counts / _all / _fill / _get / _put.
-
-pub struct MaskedCellBuffer(CellBuffer, Mask);
-impl std::ops::Sub for &MaskedCellBuffer {                                    // src/masked/masked_buffer.rs:326-336
-    type Output = MaskedCellBuffer;
-    fn sub(self, rhs: Self) -> MaskedCellBuffer {
-        let (mut b, mut m) = (ptr::null_mut(), ptr::null_mut());
-        check(unsafe { ec_masked_binary(1, (self.0).0, (self.1).0, (rhs.0).0, (rhs.1).0, &mut b, &mut m) }).unwrap();
-        MaskedCellBuffer(CellBuffer(b), Mask(m))
+cb_bin_op!(Add, add, 0);
+cb_bin_op!(Sub, sub, 1);
+cb_bin_op!(Mul, mul, 2);
+cb_bin_op!(Div, div, 3);
+impl Neg for &CellBuffer {
+    type Output = CellBuffer;
+    fn neg(self) -> CellBuffer {
+        let mut h = ptr::null_mut();
+        check(unsafe { ec_buf_neg(self.0, &mut h) }).unwrap();
+        CellBuffer(h)
     }
 }
-// from_vec_with_nodata -> ec_mask_from_nodata; to_vec_with_nodata -> ec_buf_fill_nodata + ec_buf_to_host;
-// min_max -> ec_buf_min_max(buf, mask); counts -> ec_mask_counts.
+impl Neg for CellBuffer {
+    type Output = CellBuffer;
+    fn neg(self) -> CellBuffer {
+        Neg::neg(&self)
+    }
+}
+impl Ord for CellBuffer {
+    // src/buffer.rs:390-436 on the device: first differing cell, then total order of that pair, then length
+    fn cmp(&self, o: &Self) -> Ordering {
+        let mut r = 0;
+        check(unsafe { ec_buf_cmp(self.0, o.0, &mut r) }).unwrap();
+        ordering(r)
+    }
+}
+impl PartialOrd for CellBuffer {
+    fn partial_cmp(&self, o: &Self) -> Option<Ordering> {
+        Some(self.cmp(o))
+    }
+}
+impl PartialEq for CellBuffer {
+    fn eq(&self, o: &Self) -> bool {
+        self.cmp(o) == Ordering::Equal
+    }
+}
+impl Eq for CellBuffer {}
+
+// ---- Mask — was `Mask(Vec<bool>)` (src/masked/mask.rs:12): packed bits on the device ------------------------
+/// `Index/IndexMut -> &bool` and `iter_mut` cannot point into packed device bits: they go through a host mirror
+/// (`to_vec` = ec_mask_to_bools, write back with `Mask::new`), see INTEGRATION.md §4.
+pub struct Mask(*mut ec_mask);
+unsafe impl Send for Mask {}
+unsafe impl Sync for Mask {}
+impl Drop for Mask {
+    fn drop(&mut self) {
+        unsafe { ec_mask_free(self.0) }
+    }
+}
+impl Clone for Mask {
+    fn clone(&self) -> Self {
+        let mut h = ptr::null_mut();
+        check(unsafe { ec_mask_clone(self.0, &mut h) }).unwrap();
+        Self(h)
+    }
+}
+impl Mask {
+    pub fn new(values: Vec<bool>) -> Self {
+        let mut h = ptr::null_mut();
+        check(unsafe { ec_mask_from_bools(values.as_ptr().cast(), values.len(), &mut h) }).unwrap(); // bool is one byte, 0/1
+        check(unsafe { ec_synchronize() }).unwrap();
+        Self(h)
+    }
+    pub fn fill(len: usize, value: bool) -> Self {
+        let mut h = ptr::null_mut();
+        check(unsafe { ec_mask_fill(len, value as i32, &mut h) }).unwrap();
+        Self(h)
+    }
+    pub fn fill_via<F: Fn(usize) -> bool>(len: usize, f: F) -> Self {
+        Self::new((0..len).map(f).collect())
+    }
+    pub fn len(&self) -> usize {
+        unsafe { ec_mask_len(self.0) }
+    }
+    pub fn is_empty(&self) -> bool {
+        self.len() == 0
+    }
+    pub fn put(&mut self, index: usize, value: bool) {
+        check(unsafe { ec_mask_put(self.0, index, value as i32) }).unwrap()
+    }
+    pub fn get(&self, index: usize) -> bool {
+        let mut o = 0;
+        check(unsafe { ec_mask_get(self.0, index, &mut o) }).unwrap();
+        o != 0
+    }
+    pub fn all(&self, value: bool) -> bool {
+        let mut o = 0;
+        check(unsafe { ec_mask_all(self.0, value as i32, &mut o) }).unwrap();
+        o != 0
+    }
+    pub fn counts(&self) -> (usize, usize) {
+        let (mut d, mut n) = (0usize, 0usize);
+        check(unsafe { ec_mask_counts(self.0, &mut d, &mut n) }).unwrap();
+        (d, n)
+    }
+    pub fn to_vec(&self) -> Vec<bool> {
+        let mut out = vec![false; self.len()];
+        check(unsafe { ec_mask_to_bools(self.0, out.as_mut_ptr().cast(), out.len()) }).unwrap();
+        out
+    }
+}
+macro_rules! mask_op {
+    ($trt:ident, $mth:ident, $f:ident) => {
+        impl $trt for &Mask {
+            type Output = Mask;
+            fn $mth(self, rhs: Self) -> Mask {
+                let mut h = ptr::null_mut();
+                check(unsafe { $f(self.0, rhs.0, &mut h) }).unwrap();
+                Mask(h)
+            }
+        }
+        impl $trt for Mask {
+            type Output = Mask;
+            fn $mth(self, rhs: Self) -> Mask {
+                $trt::$mth(&self, &rhs)
+            }
+        }
+    };
+}
+mask_op!(BitAnd, bitand, ec_mask_and); // src/masked/mask.rs:118-140
+mask_op!(BitOr, bitor, ec_mask_or); // src/masked/mask.rs:142-164
+impl Not for &Mask {
+    type Output = Mask;
+    fn not(self) -> Mask {
+        let mut h = ptr::null_mut();
+        check(unsafe { ec_mask_not(self.0, &mut h) }).unwrap();
+        Mask(h)
+    }
+}
+impl PartialEq for Mask {
+    fn eq(&self, o: &Self) -> bool {
+        let mut r = 0;
+        check(unsafe { ec_mask_cmp(self.0, o.0, &mut r) }).unwrap();
+        r == 0
+    }
+}
+
+// ---- MaskedCellBuffer — src/masked/masked_buffer.rs ------------------------------------------------------------
+fn nodata_ffi<T: CellEncoding>(nd: NoData<T>) -> (i32, ec_value) {
+    match nd {
+        NoData::None => (0, to_ffi(T::zero().into_cell_value())),
+        NoData::Default => (1, to_ffi(T::zero().into_cell_value())),
+        NoData::Value(v) => (2, to_ffi(v.into_cell_value())),
+    }
+}
+#[derive(Clone, PartialEq)]
+pub struct MaskedCellBuffer(CellBuffer, Mask);
+impl MaskedCellBuffer {
+    pub fn new(buffer: CellBuffer, mask: Mask) -> Self {
+        assert_eq!(buffer.len(), mask.len(), "Mask and buffer must have the same length.");
+        Self(buffer, mask)
+    }
+    /// src/masked/masked_buffer.rs:62-71 — the sentinel compare runs on the device and emits packed words
+    pub fn from_vec_with_nodata<T: CellEncoding>(data: Vec<T>, nodata: NoData<T>) -> Self {
+        let buf = CellBuffer::from_vec(data);
+        let (kind, v) = nodata_ffi(nodata);
+        let mut m = ptr::null_mut();
+        check(unsafe { ec_mask_from_nodata(buf.0, kind, &v, &mut m) }).unwrap();
+        Self(buf, Mask(m))
+    }
+    pub fn buffer(&self) -> &CellBuffer {
+        &self.0
+    }
+    pub fn mask(&self) -> &Mask {
+        &self.1
+    }
+    pub fn counts(&self) -> (usize, usize) {
+        self.1.counts()
+    }
+    pub fn get_masked(&self, index: usize) -> Option<CellValue> {
+        if self.1.get(index) { Some(self.0.get(index)) } else { None }
+    }
+    /// src/masked/masked_buffer.rs:137-152 — convert + fill fused into one pass, then one D2H copy
+    pub fn to_vec_with_nodata<T: CellEncoding>(self, no_data: NoData<T>) -> Result<Vec<T>> {
+        let (kind, v) = nodata_ffi(no_data);
+        let mut h = ptr::null_mut();
+        check(unsafe { ec_buf_fill_nodata((self.0).0, (self.1).0, T::cell_type() as u8, kind, &v, &mut h) })?;
+        CellBuffer(h).to_vec::<T>()
+    }
+    /// src/masked/masked_buffer.rs:208-217
+    pub fn min_max(&self) -> (CellValue, CellValue) {
+        let (mut a, mut b) = (ec_value { ct: 0, pad: [0; 7], bits: 0 }, ec_value { ct: 0, pad: [0; 7], bits: 0 });
+        check(unsafe { ec_buf_min_max((self.0).0, (self.1).0, &mut a, &mut b) }).unwrap();
+        (from_ffi(a), from_ffi(b))
+    }
+}
+macro_rules! mcb_bin_op {
+    // src/masked/masked_buffer.rs:323-370: data on all cells, mask = lmask & rmask, one fused launch
+    ($trt:ident, $mth:ident, $code:expr) => {
+        impl $trt for &MaskedCellBuffer {
+            type Output = MaskedCellBuffer;
+            fn $mth(self, rhs: Self) -> MaskedCellBuffer {
+                let (mut b, mut m) = (ptr::null_mut(), ptr::null_mut());
+                check(unsafe { ec_masked_binary($code, (self.0).0, (self.1).0, (rhs.0).0, (rhs.1).0, &mut b, &mut m) }).unwrap();
+                MaskedCellBuffer(CellBuffer(b), Mask(m))
+            }
+        }
+        impl $trt for MaskedCellBuffer {
+            type Output = MaskedCellBuffer;
+            fn $mth(self, rhs: Self) -> MaskedCellBuffer {
+                $trt::$mth(&self, &rhs)
+            }
+        }
+        impl<R: Into<CellValue>> $trt<R> for MaskedCellBuffer {
+            type Output = MaskedCellBuffer;
+            fn $mth(self, rhs: R) -> MaskedCellBuffer {
+                let MaskedCellBuffer(buf, mask) = self;
+                MaskedCellBuffer($trt::$mth(buf, rhs), mask) // the mask moves through unchanged (:353-364)
+            }
+        }
+    };
+}
+mcb_bin_op!(Add, add, 0);
+mcb_bin_op!(Sub, sub, 1);
+mcb_bin_op!(Mul, mul, 2);
+mcb_bin_op!(Div, div, 3);
