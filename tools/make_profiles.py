@@ -94,18 +94,22 @@ def launch_list():
     open(os.path.join(P, f"{R}_launches_bench.csv"), "w").write("".join(lines))
 
 
-# ---- ncu --set full over one launch of each kernel family -------------------------------------------
+# ---- ncu --set full over one launch of each kernel family, and over one whole step of bench.py ---------
 def full():
-    path = os.path.join(G, f"prof_{R}_ops.ncu-rep")
-    if not os.path.exists(path):
-        return
-    txt = capture(ncu_summary.raw, path)
-    hdr = (f"# {R} — `ncu --set full --clock-control none --import-source on` over `python tools/profile_ops.py`\n\n"
-           "One launch of each kernel family on 8192^2-cell buffers (the .ncu-rep itself is 59 MB and stays in gpurun_out/).\n"
-           "dram % is of ncu's peak (8.18 TB/s = 3996 MHz x 8192 bit x 2); the copy peak measured on this pool is 6.53 TB/s = 80 % of it.\n\n")
-    open(os.path.join(P, f"{R}_ncu_full_ops.md"), "w").write(hdr + txt)
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    open(os.path.join(P, f"{R}_ncu_full_ops_raw.csv"), "w").write(raw)
+    for src, dst, title, note in (
+        ("ops_full_raw.csv", f"{R}_ncu_full_ops", "`ncu --set full --clock-control none` over `python tools/profile_ops.py`",
+         "One launch of each kernel family on 8192^2-cell buffers."),
+        ("bench_step_full_raw.csv", f"{R}_ncu_full_bench_step",
+         "`ncu --set full --clock-control none -k regex:map1_kernel -s 240 -c 41` over `python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-configs`",
+         "The 41 launches of one timed step of the headline workload (31 casts + 10 clones).")):
+        path = os.path.join(G, src)
+        if not os.path.exists(path):
+            continue
+        txt = capture(ncu_summary.raw, path)
+        hdr = (f"# {R} — {title}\n\n{note} Raw page as CSV next to this file (the .ncu-rep files exceed gpurun's 64 MiB return limit).\n"
+               "dram % is of ncu's peak (8.18 TB/s = 3996 MHz x 8192 bit x 2); the copy peak measured on this pool is 6.53 TB/s = 80 % of it.\n\n")
+        open(os.path.join(P, dst + ".md"), "w").write(hdr + txt)
+        open(os.path.join(P, dst + "_raw.csv"), "w").write("".join(l for l in open(path) if l.strip() and not l.startswith("==")))
 
 
 ubench()

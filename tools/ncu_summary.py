@@ -63,7 +63,11 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def raw(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """`path`: a .ncu-rep, or the CSV that `ncu --csv --page raw --log-file` wrote."""
+    if path.endswith(".csv"):
+        out = "".join(l for l in open(path) if l.strip() and not l.startswith("=="))
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rd = csv.reader(io.StringIO(out))
     header = next(rd)
     units = next(rd)
