@@ -38,10 +38,24 @@ __global__ void __launch_bounds__(THREADS) mask_build_kernel(const U* __restrict
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             uint32_t bits = 0;
+            if constexpr (sizeof(U) == 1 && V == 32) {
+                // 8-bit cells, four at a time: "byte != sentinel" as a SWAR test (high bit of each byte set iff the xor is
+                // non-zero), the four flags gathered into a nibble with one multiply — 2 instructions per cell instead of 3
+                const uint32_t s4 = PACK_BOOLS ? 0u : static_cast<uint32_t>(sentinel) * 0x01010101u;
+                uint32_t words[8];
+                memcpy(words, &va[u], 32);
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-                const bool valid = PACK_BOOLS ? (va[u].v[j] != U(0)) : (va[u].v[j] != sentinel);
-                bits |= static_cast<uint32_t>(valid) << j;
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t d = words[q] ^ s4;
+                    const uint32_t nz = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
+                    bits |= ((((nz >> 7) * 0x01020408u) >> 24) & 0xFu) << (4 * q);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const bool valid = PACK_BOOLS ? (va[u].v[j] != U(0)) : (va[u].v[j] != sentinel);
+                    bits |= static_cast<uint32_t>(valid) << j;
+                }
             }
             const uint32_t w = assemble_word<V>(bits, lane);
             if (lane % TPW == 0) out[(base + size_t(u) * THREADS * V) / 32] = w;

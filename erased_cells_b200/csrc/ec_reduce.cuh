@@ -163,7 +163,45 @@ __global__ void __launch_bounds__(THREADS) min_max_kernel(const T* __restrict__ 
     const size_t full = n / TILE;
     K kmin = seed_min, kmax = seed_max;
 
-    if constexpr (!MASKED && sizeof(T) <= 2) {
+    if constexpr (MASKED && sizeof(T) == 1 && VB == 32) {
+        // 8-bit cells with a mask: a thread's 32 cells are exactly one mask word. Invalid bytes are forced to the
+        // identity of the biased unsigned domain (0xFF for min, 0x00 for max — which are also the seeds T::MAX /
+        // T::MIN), then the same packed 16-bit-lane min/max as the unmasked path.
+        constexpr bool SG = std::is_signed<T>::value;
+        constexpr uint32_t BIAS = SG ? 0x80808080u : 0u;
+        uint32_t pmin = 0xFFFFFFFFu, pmax = 0u;
+        for (size_t t = blockIdx.x; t < full; t += gridDim.x) {
+            const size_t base = t * TILE + size_t(threadIdx.x) * V;
+            Vec<uint32_t, 8> w[UNROLL];
+            uint32_t mw[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const size_t c = base + size_t(u) * THREADS * V;
+                w[u] = ld_stream<uint32_t, 8>(reinterpret_cast<const uint32_t*>(a + c));
+                mw[u] = __ldg(m + c / 32);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t nib = (mw[u] >> (4 * j)) & 0xFu;
+                    const uint32_t sel = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;  // 4 mask bits -> 4 byte masks
+                    const uint32_t x = w[u].v[j] ^ BIAS;
+                    const uint32_t xmin = x | ~sel, xmax = x & sel;
+                    pmin = __vimin3_u16x2(pmin, __byte_perm(xmin, 0u, 0x4240), __byte_perm(xmin, 0u, 0x4341));
+                    pmax = __vimax3_u16x2(pmax, __byte_perm(xmax, 0u, 0x4240), __byte_perm(xmax, 0u, 0x4341));
+                }
+            }
+        }
+        constexpr uint32_t LB = SG ? 0x80u : 0u;
+        const uint32_t lo = min(pmin & 0xFFFFu, pmin >> 16), hi = max(pmax & 0xFFFFu, pmax >> 16);
+        if (full > 0 && blockIdx.x < full) {
+            const T vlo = static_cast<T>(static_cast<bits_t<T>>(lo ^ LB)), vhi = static_cast<T>(static_cast<bits_t<T>>(hi ^ LB));
+            const K klo = to_key<T>(vlo), khi = to_key<T>(vhi);
+            kmin = klo < kmin ? klo : kmin;
+            kmax = khi > kmax ? khi : kmax;
+        }
+    } else if constexpr (!MASKED && sizeof(T) <= 2) {
         constexpr bool SG = std::is_signed<T>::value;
         constexpr uint32_t BIAS = sizeof(T) == 1 ? (SG ? 0x80808080u : 0u) : (SG ? 0x80008000u : 0u);
         uint32_t pmin = 0xFFFFFFFFu, pmax = 0u;  // two 16-bit lanes of biased keys
@@ -265,11 +303,18 @@ __global__ void __launch_bounds__(THREADS) first_diff_kernel(const T* __restrict
     constexpr int V = VB / sizeof(T);
     uint64_t first = ~0ull;
     const size_t groups = n / V;
+    // compare 32 bytes as four 64-bit words; only a differing word is examined cell by cell (lowest differing byte)
     for (size_t g = blockIdx.x * size_t(THREADS) + threadIdx.x; g < groups; g += size_t(gridDim.x) * THREADS) {
-        const Vec<T, V> x = ld_stream<T, V>(a + g * V), y = ld_stream<T, V>(b + g * V);
+        const Raw<VB> x = ld_stream_raw<VB>(a + g * V), y = ld_stream_raw<VB>(b + g * V);
+        static_assert(VB == 32, "first_diff_kernel compares 4 x 64-bit words per thread");
 #pragma unroll
-        for (int j = V - 1; j >= 0; --j)
-            if (to_bits(x.v[j]) != to_bits(y.v[j])) { const uint64_t i = g * V + j; first = i < first ? i : first; }
+        for (int w = 3; w >= 0; --w) {
+            const uint64_t d = x.r[w] ^ y.r[w];
+            if (d != 0) {
+                const uint64_t i = g * V + (w * 8 + (__ffsll(static_cast<long long>(d)) - 1) / 8) / sizeof(T);
+                first = i < first ? i : first;
+            }
+        }
     }
     if (blockIdx.x == 0)
         for (size_t i = groups * V + threadIdx.x; i < n; i += THREADS)

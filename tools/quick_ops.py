@@ -33,7 +33,14 @@ def row(name, ms, bpc):
     print(f"{name:46s} {ms:8.3f} ms  {bpc * N / ms / 1e6:8.0f} GB/s")
 
 
-mask_h = synth.device(T.UInt8, N, 99)
+def _fill(m, ct):
+    h = C.c_void_p()
+    nd = NoData.new(ct, 1)
+    ec._lib.check(L.ec_buf_fill_nodata(m.buffer()._h, m.mask()._h, int(ct), nd.kind, nd._ptr(), C.byref(h)))
+    return h
+
+
+
 for ct in (T.UInt8, T.Int8, T.UInt16, T.Int16, T.UInt32, T.Float32, T.Int64, T.Float64):
     a = synth.device(ct, N, 1 + int(ct))
     sz = ct.size_of()
@@ -47,13 +54,6 @@ for ct in (T.UInt8, T.Int8, T.UInt16, T.Int16, T.UInt32, T.Float32, T.Int64, T.F
     row(f"scalar mul {ct}", timed(lambda: a * 0.5), sz + 8)
     row(f"fill {ct}", timed(lambda: CellBuffer.fill(N, CellValue(ct, 3))), sz)
     del a, m
-
-
-def _fill(m, ct):
-    h = C.c_void_p()
-    nd = NoData.new(ct, 1)
-    ec._lib.check(L.ec_buf_fill_nodata(m.buffer()._h, m.mask()._h, int(ct), nd.kind, nd._ptr(), C.byref(h)))
-    return h
 
 
 ma, mb = Mask.new(synth.host(T.UInt8, 1 << 20, 1) < 128), None
