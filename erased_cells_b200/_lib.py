@@ -116,6 +116,7 @@ def _signatures():
         "ec_buf_with_defaults": (S, [SZ, U8, PVP]),
         "ec_buf_fill": (S, [SZ, PV, PVP]),
         "ec_buf_wrap_device": (S, [U8, VP, SZ, PVP]),
+        "ec_buf_view": (S, [VP, SZ, SZ, PVP]),
         "ec_buf_clone": (S, [VP, PVP]),
         "ec_buf_free": (None, [VP]),
         "ec_buf_len": (SZ, [VP]),

@@ -356,6 +356,12 @@ class CellBuffer:
         check(lib().ec_buf_clone(self._h, C.byref(h)))
         return CellBuffer._take(h)
 
+    def view(self, offset: int, len_: int) -> "CellBuffer":
+        """Cells [offset, offset + len) as a buffer sharing this allocation (a row strip); offset on a 32-byte boundary."""
+        h = C.c_void_p()
+        check(lib().ec_buf_view(self._h, offset, len_, C.byref(h)))
+        return CellBuffer._take(h)
+
     def __iter__(self):
         """IntoIterator for &CellBuffer (src/buffer.rs:278-305): yields CellValues from a host copy."""
         ct = self.cell_type()

@@ -1010,6 +1010,16 @@ ec_status ec_buf_wrap_device(uint8_t ct, void* device_ptr, size_t len, ec_buf** 
     *out = new ec_buf{ct, false, len, len * kSize[ct], device_ptr, nullptr, nullptr, nullptr};
     return EC_OK;
 }
+ec_status ec_buf_view(const ec_buf* b, size_t offset_cells, size_t len, ec_buf** out) {
+    EC_TRY(ensure());
+    EC_TRY(resolve(b));
+    if (offset_cells > b->len || len > b->len - offset_cells) { set_error("view [%zu, %zu) outside a buffer of %zu cells", offset_cells, offset_cells + len, b->len); return EC_OOB; }
+    if ((offset_cells * kSize[b->ct]) % 32 != 0) return invalid("a view must start on a 32-byte boundary (row strips start on 128-cell boundaries)");
+    ec_buf* v = new ec_buf{b->ct, b->owned, len, len * kSize[b->ct], static_cast<char*>(b->dptr) + offset_cells * kSize[b->ct], nullptr, b->blk, nullptr};
+    if (b->ready) cudaStreamWaitEvent(cur_stream(), b->ready, 0);  // the view has no event of its own: order it after the upload now
+    *out = v;
+    return EC_OK;
+}
 ec_status ec_buf_clone(const ec_buf* b, ec_buf** out) {
     EC_TRY(ensure());
     EC_TRY(resolve(b));

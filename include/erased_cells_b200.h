@@ -160,6 +160,9 @@ ec_status ec_buf_with_defaults(size_t len, uint8_t ct, ec_buf** out);
 ec_status ec_buf_fill(size_t len, const ec_value* value, ec_buf** out);
 /* wrap caller-owned device memory (row strip of a raster already in HBM); not freed by ec_buf_free */
 ec_status ec_buf_wrap_device(uint8_t ct, void* device_ptr, size_t len, ec_buf** out);
+/* a row strip (or any 32-byte aligned sub-range) of a buffer as a buffer of its own: shares the allocation
+ * (refcounted), no copy; in-place mutation through either handle copies first */
+ec_status ec_buf_view(const ec_buf* b, size_t offset_cells, size_t len, ec_buf** out);
 ec_status ec_buf_clone(const ec_buf* b, ec_buf** out);   /* #[derive(Clone)] (:50) */
 void ec_buf_free(ec_buf* b);                             /* Drop */
 size_t ec_buf_len(const ec_buf* b);                      /* :90-99 */

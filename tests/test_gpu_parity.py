@@ -483,3 +483,27 @@ def test_lazy_expression_vm_matches_eager(orc):
     for i in range(60):
         y = y * 1.0001 + dev[4]
     assert x == y
+
+
+def test_views_share_the_allocation(orc):
+    """ec_buf_view: a strip of a resident raster as a buffer of its own — no copy, refcounted, copy on write."""
+    n = 4 * 32768
+    h = synth.host(CellType.Int16, n, 0x51E)
+    whole = CellBuffer.from_vec(h)
+    strips = [whole.view(g * 32768, 32768) for g in range(4)]
+    for g, s in enumerate(strips):
+        assert s.len() == 32768 and s.device_ptr() == whole.device_ptr() + g * 32768 * 2
+        assert np.array_equal(s.to_vec(), h[g * 32768:(g + 1) * 32768])
+        mn, mx = s.min_max()
+        omn, omx = orc.tight_min_max(h[g * 32768:(g + 1) * 32768])
+        assert (mn.bits, mx.bits) == (omn.bits, omx.bits)
+    tail = whole.view(3 * 32768 + 128, 32768 - 128)          # any 32-byte aligned start
+    assert np.array_equal(tail.to_vec(), h[3 * 32768 + 128:])
+    del whole                                                 # the strips keep the allocation alive
+    assert np.array_equal((strips[1] - strips[2]).to_vec(), orc.tight_binary(orc.SUB, h[32768:65536], h[65536:98304]))
+    strips[0].put(5, CellValue(CellType.Int16, 1234))         # mutation through a view copies first
+    assert strips[0].get(5).value() == 1234 and np.array_equal(strips[1].to_vec(), h[32768:65536])
+    with pytest.raises(IndexError):
+        strips[0].view(32768, 1)
+    with pytest.raises(ec.EcError):
+        strips[0].view(3, 10)
