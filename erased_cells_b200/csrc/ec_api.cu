@@ -473,10 +473,11 @@ cudaError_t launch_binary_scalar(const Launch& L, int op1, int lct, const void* 
 
 // ---- lazy op chains ---------------------------------------------------------
 // With ec_set_lazy(1) the arithmetic operators return a buffer whose value is a pending Expr over
-// refcounted snapshots of its operands. The first access evaluates it and recognises two shapes that
+// refcounted snapshots of its operands. The first access evaluates it and recognises three shapes that
 // would otherwise cost extra passes over HBM:
 //     (X - Y) / (X + Y)      -> one normalized-difference kernel  (48 -> 12 B/cell for u16 NDVI)
 //     (X op1 Y) op2 scalar   -> one binary-then-scalar kernel      (27 -> 11 B/cell for u8/u16*0.5)
+//     (X op1 s1) op2 s2      -> one scale-and-offset kernel        (26 -> 10 B/cell for u16 * gain + offset)
 // Every op keeps its own IEEE rounding, so results are bit-identical to eager evaluation. Operands are
 // immutable snapshots: put/extend on a buffer that a pending Expr still references copy it first.
 static thread_local int t_lazy = 0;  // 0 eager, 1 deferred with the dedicated fused shapes, 2 also the expression VM
@@ -606,7 +607,11 @@ static ec_status eval(Expr& e) {
     const char* family;
     Expr* cl = e.l.expr && !e.l.expr->done ? e.l.expr.get() : nullptr;
     Expr* cr = e.kind == EX_BIN && e.r.expr && !e.r.expr->done ? e.r.expr.get() : nullptr;
-    if (e.kind == EX_SCALAR && cl && cl->kind == EX_BIN) {
+    if (e.kind == EX_SCALAR && cl && cl->kind == EX_SCALAR) {  // (X op1 s1) op2 s2: scale-and-offset in one pass
+        if (ec_status s = eval_operand(cl->l)) return s;
+        err = launch_scalar_scalar(launch_ctx(), cl->op, cl->l.ct, cl->l.ptr, cl->s, e.op, e.s, static_cast<double*>(out), e.n);
+        family = "scalar_scalar(lazy)";
+    } else if (e.kind == EX_SCALAR && cl && cl->kind == EX_BIN) {
         if (ec_status s = eval_operand(cl->l)) return s;
         if (ec_status s = eval_operand(cl->r)) return s;
         err = launch_binary_scalar(launch_ctx(), cl->op, cl->l.ct, cl->l.ptr, cl->r.ct, cl->r.ptr, e.op, e.s, static_cast<double*>(out), e.n);

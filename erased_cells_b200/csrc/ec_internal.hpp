@@ -75,6 +75,7 @@ cudaError_t launch_binary_scalar(const Launch& L, int op1, int lct, const void* 
                                  double s, double* out, size_t n);
 cudaError_t launch_binary_scalar_static(const Launch& L, int op1, int lct, const void* l, int rct, const void* r, int op2,
                                         double s, double* out, size_t n);
+cudaError_t launch_scalar_scalar(const Launch& L, int op1, int ct, const void* a, double s1, int op2, double s2, double* out, size_t n);
 cudaError_t launch_vm(const Launch& L, const VmProgram& p, double* out, size_t n);
 // reductions: results land in scratch.result[0..1] (device); keys are unsigned order keys
 cudaError_t launch_min_max(const Launch& L, int ct, const void* a, const uint32_t* mask, size_t n,

@@ -65,6 +65,16 @@ template <class L, class R, int OP1, int OP2> struct BinaryScalarT {
     }
 };
 
+// `(a op1 s1) op2 s2` — scale-and-offset chains (`dn * 0.0001 + 273.15`), both ops at compile time
+template <class L, int OP1, int OP2> struct ScalarScalarT {
+    using A = L; using O = double;
+    double s1, s2;
+    __device__ __forceinline__ double operator()(L a) const {
+        const double t = f64_op<OP1, true, true>(as_f64(a), s1);
+        return f64_op<OP2, true, true>(t, s2);
+    }
+};
+
 // ---- one-input map -----------------------------------------------------------------------------
 template <class F, int VB, int UNROLL, int THREADS>
 __global__ void __launch_bounds__(THREADS) map1_kernel(const typename F::A* __restrict__ a,

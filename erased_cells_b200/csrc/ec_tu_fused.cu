@@ -55,6 +55,40 @@ cudaError_t launch_binary_scalar_static(const Launch& Lc, int op1, int lct, cons
     return cudaErrorNotSupported;
 }
 
+// ---- `(a op1 s1) op2 s2` for every cell type and all 16 (op1, op2) -----------------------------------------------
+template <class L, int OP1, int OP2>
+static cudaError_t go_ss(const Launch& Lc, const void* a, double s1, double s2, double* out, size_t n) {
+    using F = ScalarScalarT<L, OP1, OP2>;
+    constexpr int V = EC_VB / cmax<sizeof(L), 8>();
+    constexpr size_t TILE = size_t(kThreads) * V * EC_UNROLL;
+    map1_kernel<F, EC_VB, EC_UNROLL, kThreads><<<grid_for(n, TILE, Lc), kThreads, 0, Lc.stream>>>(static_cast<const L*>(a), out, n, F{s1, s2});
+    return cudaGetLastError();
+}
+template <class L, int OP1> static cudaError_t ss_op2(const Launch& Lc, int op2, const void* a, double s1, double s2, double* out, size_t n) {
+    switch (op2) {
+        case OP_ADD: return go_ss<L, OP1, OP_ADD>(Lc, a, s1, s2, out, n);
+        case OP_SUB: return go_ss<L, OP1, OP_SUB>(Lc, a, s1, s2, out, n);
+        case OP_MUL: return go_ss<L, OP1, OP_MUL>(Lc, a, s1, s2, out, n);
+        default: return go_ss<L, OP1, OP_DIV>(Lc, a, s1, s2, out, n);
+    }
+}
+template <class L> static cudaError_t ss_ops(const Launch& Lc, int op1, int op2, const void* a, double s1, double s2, double* out, size_t n) {
+    switch (op1) {
+        case OP_ADD: return ss_op2<L, OP_ADD>(Lc, op2, a, s1, s2, out, n);
+        case OP_SUB: return ss_op2<L, OP_SUB>(Lc, op2, a, s1, s2, out, n);
+        case OP_MUL: return ss_op2<L, OP_MUL>(Lc, op2, a, s1, s2, out, n);
+        default: return ss_op2<L, OP_DIV>(Lc, op2, a, s1, s2, out, n);
+    }
+}
+cudaError_t launch_scalar_scalar(const Launch& Lc, int op1, int ct, const void* a, double s1, int op2, double s2, double* out, size_t n) {
+    switch (ct) {
+#define X(id, p) case id: return ss_ops<p>(Lc, op1, op2, a, s1, s2, out, n);
+        EC_WITH_CT(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+
 cudaError_t launch_vm(const Launch& Lc, const VmProgram& p, double* out, size_t n) {
     constexpr size_t TILE = size_t(kThreads) * EC_VM_V;
     vm_kernel<kThreads><<<grid_for(n, TILE, Lc), kThreads, 0, Lc.stream>>>(p, out, n);

@@ -192,7 +192,7 @@ ec_status ec_buf_cmp(const ec_buf* l, const ec_buf* r, int* ordering);
 /* ---- fused op chains behind the same operators -------------------------
  * ec_set_lazy(1) (per thread, default 0): ec_buf_binary / ec_buf_scalar / ec_masked_binary return at once with a
  * pending result over refcounted snapshots of their operands; the first access evaluates it, fusing
- * `(X - Y) / (X + Y)` and `(X op1 Y) op2 scalar` into one pass over HBM. Results are bit-identical to eager
+ * `(X - Y) / (X + Y)`, `(X op1 Y) op2 scalar` and `(X op1 s1) op2 s2` into one pass over HBM. Results are bit-identical to eager
  * evaluation; later put/extend on an operand do not affect a pending result (copy on write).
  * ec_set_lazy(2) additionally sends longer chains through the expression VM (one interpreted pass, ec_vm.cuh) —
  * experimental: bit-identical, but measured only 1.1x faster than op-by-op evaluation on an 8-op chain. */

@@ -362,6 +362,15 @@ def test_lazy_chains_fuse_and_match_eager(orc):
             assert np.array_equal(bits(got), bits(eager_chain.to_vec()))
             want = orc.tight_binary(orc.DIV, orc.tight_binary(orc.SUB, orc.tight_scalar(orc.MUL, orc.tight_binary(orc.ADD, l, r), orc.value(orc.Float64, 2.0)), l), r)
             assert np.array_equal(bits(deep.to_vec()), bits(want))
+            # scale-and-offset: (x op1 s1) op2 s2 in one pass, for every op pair
+            for op1 in range(4):
+                for op2 in range(4):
+                    k1 = L.ec_kernel_launches()
+                    so = a._bin(op1, 0.0001)._bin(op2, 273.15)
+                    got = so.to_vec()
+                    assert L.ec_kernel_launches() == k1 + 1 and L.ec_last_kernel() == b"scalar_scalar(lazy)"
+                    w2 = orc.tight_scalar(op2, orc.tight_scalar(op1, l, orc.value(orc.Float64, 0.0001)), orc.value(orc.Float64, 273.15))
+                    assert np.array_equal(bits(got), bits(w2)), (lct, op1, op2)
             # operands are snapshots: dropping or mutating them after the fact does not change a pending result
             x, y = CellBuffer.from_vec(l), CellBuffer.from_vec(r)
             pend = (x - y) / (x + y)
