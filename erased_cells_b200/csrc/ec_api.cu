@@ -37,6 +37,7 @@ void set_error(const char* fmt, ...) {
 }
 ec_status cuda_fail(cudaError_t e, const char* what) {
     set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    cudaGetLastError();  // the error has been reported: do not let a recoverable one (e.g. out of memory) taint the next launch check
     if (e == cudaErrorMemoryAllocation) return EC_OOM;
     if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) return EC_NO_DEVICE;
     return EC_CUDA;

@@ -516,3 +516,17 @@ def test_views_share_the_allocation(orc):
         strips[0].view(32768, 1)
     with pytest.raises(ec.EcError):
         strips[0].view(3, 10)
+
+
+def test_allocation_failure_and_trim():
+    """An impossible allocation is an error code (MemoryError here), not a crash; the block cache can be handed back."""
+    L = ec.lib()
+    with pytest.raises(MemoryError):
+        CellBuffer.with_defaults(1 << 42, CellType.Float64)      # 32 TiB
+    a = CellBuffer.with_defaults(1 << 24, CellType.UInt8)          # the library is still usable afterwards
+    assert a.min_max()[1].value() == 0
+    del a
+    assert L.ec_cached_bytes() >= (1 << 24)
+    ec._lib.check(L.ec_trim())
+    assert L.ec_cached_bytes() == 0
+    assert CellBuffer.fill(100, CellValue(CellType.Int32, 7)).get(99).value() == 7
