@@ -210,6 +210,16 @@ struct DevBlock {
     DevBlock& operator=(const DevBlock&) = delete;
     ~DevBlock() { dev_free(p); }
 };
+// scoped owners for temporaries and half-built results: an early error return must not leak device memory
+struct Scratch {
+    void* p = nullptr;
+    Scratch() = default;
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
+    ~Scratch() { dev_free(p); }
+    ec_status alloc(size_t bytes) { return dev_alloc(&p, bytes); }
+    void* release() { void* q = p; p = nullptr; return q; }
+};
 static ec_status sync_stream() {
     if (cudaError_t e = cudaStreamSynchronize(cur_stream())) return cuda_fail(e, "cudaStreamSynchronize");
     return EC_OK;
@@ -1090,39 +1100,33 @@ ec_status ec_buf_extend_host(ec_buf* b, uint8_t ct, const void* host, size_t n) 
     if (n == 0) return EC_OK;
     EC_TRY(resolve(b));
     const size_t new_len = b->len + n, sz = kSize[b->ct];
-    void* grown;
-    EC_TRY(dev_alloc(&grown, new_len * sz));
-    if (b->len) EC_CUDA_TRY(cudaMemcpyAsync(grown, rd(b), b->len * sz, cudaMemcpyDeviceToDevice, cur_stream()), "cudaMemcpyAsync(D2D)");
-    char* dst = static_cast<char*>(grown) + b->len * sz;
-    bool failed = false;
-    if (ct == b->ct && !(ct == EC_FLOAT32)) {  // same type: to_<p>() is the identity (f32 NaNs still pass through f64, below)
+    Scratch grown;
+    EC_TRY(grown.alloc(new_len * sz));
+    if (b->len) EC_CUDA_TRY(cudaMemcpyAsync(grown.p, rd(b), b->len * sz, cudaMemcpyDeviceToDevice, cur_stream()), "cudaMemcpyAsync(D2D)");
+    char* dst = static_cast<char*>(grown.p) + b->len * sz;
+    if (ct == b->ct && ct != EC_FLOAT32) {  // same type: to_<p>() is the identity (f32 NaNs still pass through f64, below)
         EC_CUDA_TRY(cudaMemcpyAsync(dst, host, n * sz, cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
         EC_TRY(sync_stream());
     } else {
         // `c.into_cell_value().to_<p>().unwrap()` (src/buffer.rs:212): value-checked on the device
-        void *stage, *conv;
-        EC_TRY(dev_alloc(&stage, n * kSize[ct]));
-        EC_TRY(dev_alloc(&conv, n * sz));  // the appended run starts at an arbitrary cell offset: cast into an aligned temp
+        Scratch stage, conv;  // the appended run starts at an arbitrary cell offset: cast into an aligned temp
+        EC_TRY(stage.alloc(n * kSize[ct]));
+        EC_TRY(conv.alloc(n * sz));
         ReduceScratch sc;
         EC_TRY(reduce_scratch(&sc));
-        EC_CUDA_TRY(cudaMemcpyAsync(stage, host, n * kSize[ct], cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
+        EC_CUDA_TRY(cudaMemcpyAsync(stage.p, host, n * kSize[ct], cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
         EC_CUDA_TRY(cudaMemsetAsync(sc.result, 0, 8, cur_stream()), "cudaMemsetAsync");
-        EC_LAUNCH(launch_checked_cast(launch_ctx(), ct, stage, b->ct, conv, n, reinterpret_cast<unsigned int*>(sc.result)), "checked_cast");
-        EC_CUDA_TRY(cudaMemcpyAsync(dst, conv, n * sz, cudaMemcpyDeviceToDevice, cur_stream()), "cudaMemcpyAsync(D2D)");
+        EC_LAUNCH(launch_checked_cast(launch_ctx(), ct, stage.p, b->ct, conv.p, n, reinterpret_cast<unsigned int*>(sc.result)), "checked_cast");
+        EC_CUDA_TRY(cudaMemcpyAsync(dst, conv.p, n * sz, cudaMemcpyDeviceToDevice, cur_stream()), "cudaMemcpyAsync(D2D)");
         uint64_t* pin;
         EC_TRY(pinned_words(&pin));
         EC_CUDA_TRY(cudaMemcpyAsync(pin, sc.result, 8, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
         EC_TRY(sync_stream());  // `host` may be reused by the caller as soon as we return
-        failed = (pin[0] & 0xFFFFFFFFu) != 0;
-        dev_free(stage);
-        dev_free(conv);
+        if ((pin[0] & 0xFFFFFFFFu) != 0) return narrowing(ct, b->ct);  // a cell did not fit: the reference panics in `unwrap()`; the buffer is left untouched
     }
-    if (failed) {  // a cell did not fit: the reference panics in `unwrap()`; the buffer is left untouched
-        dev_free(grown);
-        return narrowing(ct, b->ct);
-    }
-    b->blk = std::make_shared<DevBlock>(grown);  // the old block returns to the allocator once no pending Expr needs it
-    b->dptr = grown;
+    void* p = grown.release();
+    b->blk = std::make_shared<DevBlock>(p);  // the old block returns to the allocator once no pending Expr needs it
+    b->dptr = p;
     b->len = new_len;
     b->capacity_bytes = new_len * sz;
     return EC_OK;
@@ -1275,14 +1279,14 @@ ec_status ec_mask_from_bools(const uint8_t* host_bools, size_t len, ec_mask** ou
     EC_TRY(ensure());
     ec_mask* m;
     EC_TRY(new_mask(len, &m));
+    std::unique_ptr<ec_mask, void (*)(ec_mask*)> hold(m, ec_mask_free);
     if (len) {
-        void* stage;
-        EC_TRY(dev_alloc(&stage, len));
-        EC_CUDA_TRY(cudaMemcpyAsync(stage, host_bools, len, cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
-        EC_LAUNCH(launch_mask_build(launch_ctx(), 1, stage, len, 0, true, m->words), "mask_pack");
-        dev_free(stage);
+        Scratch stage;
+        EC_TRY(stage.alloc(len));
+        EC_CUDA_TRY(cudaMemcpyAsync(stage.p, host_bools, len, cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
+        EC_LAUNCH(launch_mask_build(launch_ctx(), 1, stage.p, len, 0, true, m->words), "mask_pack");
     }
-    *out = m;
+    *out = hold.release();
     return EC_OK;
 }
 ec_status ec_mask_fill(size_t len, int value, ec_mask** out) {
@@ -1297,11 +1301,10 @@ ec_status ec_mask_to_bools(const ec_mask* m, uint8_t* host_bools, size_t capacit
     EC_TRY(ensure());
     if (capacity < m->len) return invalid("ec_mask_to_bools: host buffer too small");
     if (m->len == 0) return EC_OK;
-    void* stage;
-    EC_TRY(dev_alloc(&stage, m->len));
-    EC_LAUNCH(launch_mask_unpack(launch_ctx(), m->words, m->len, static_cast<uint8_t*>(stage)), "mask_unpack");
-    EC_CUDA_TRY(cudaMemcpyAsync(host_bools, stage, m->len, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
-    dev_free(stage);
+    Scratch stage;
+    EC_TRY(stage.alloc(m->len));
+    EC_LAUNCH(launch_mask_unpack(launch_ctx(), m->words, m->len, static_cast<uint8_t*>(stage.p)), "mask_unpack");
+    EC_CUDA_TRY(cudaMemcpyAsync(host_bools, stage.p, m->len, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
     return sync_stream();
 }
 ec_status ec_mask_clone(const ec_mask* m, ec_mask** out) {
@@ -1353,17 +1356,15 @@ ec_status ec_mask_extend_host(ec_mask* m, const uint8_t* host_bools, size_t n) {
     if (n == 0) return EC_OK;
     // unpack -> append -> repack on the device (Extend is not a bulk path in the reference either)
     const size_t new_len = m->len + n;
-    void* stage;
-    EC_TRY(dev_alloc(&stage, new_len));
-    if (m->len) EC_LAUNCH(launch_mask_unpack(launch_ctx(), m->words, m->len, static_cast<uint8_t*>(stage)), "mask_unpack");
-    EC_CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(stage) + m->len, host_bools, n, cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
-    void* words;
-    EC_TRY(dev_alloc(&words, mask_bytes(new_len)));
-    EC_LAUNCH(launch_mask_build(launch_ctx(), 1, stage, new_len, 0, true, static_cast<uint32_t*>(words)), "mask_pack");
-    dev_free(stage);
-    EC_TRY(sync_stream());
+    Scratch stage, words;
+    EC_TRY(stage.alloc(new_len));
+    if (m->len) EC_LAUNCH(launch_mask_unpack(launch_ctx(), m->words, m->len, static_cast<uint8_t*>(stage.p)), "mask_unpack");
+    EC_CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(stage.p) + m->len, host_bools, n, cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
+    EC_TRY(words.alloc(mask_bytes(new_len)));
+    EC_LAUNCH(launch_mask_build(launch_ctx(), 1, stage.p, new_len, 0, true, static_cast<uint32_t*>(words.p)), "mask_pack");
+    EC_TRY(sync_stream());  // `host_bools` may be reused by the caller as soon as we return
     dev_free(m->words);
-    m->words = static_cast<uint32_t*>(words);
+    m->words = static_cast<uint32_t*>(words.release());
     m->len = new_len;
     m->capacity_bytes = mask_bytes(new_len);
     return EC_OK;
