@@ -5,7 +5,7 @@ The product is ``lib/liberased_cells_b200.so`` (hand-written sm_100a kernels beh
 used by the parity tests and the bench. Nothing here computes cells on the CPU.
 """
 from ._lib import EcError, NarrowingError, NoDeviceError, ParseError, build, lib  # noqa: F401
-from .api import CellBuffer, CellType, CellValue, Mask, MaskedCellBuffer, NoData, from_serde, to_serde  # noqa: F401
+from .api import CellBuffer, CellType, CellValue, Mask, MaskedCellBuffer, NoData, Statistics, from_serde, to_serde  # noqa: F401
 
 import contextlib as _contextlib
 
@@ -25,5 +25,5 @@ def lazy(on: bool = True, vm: bool = False):
     finally:
         check(lib().ec_set_lazy(prev))
 
-__all__ = ["CellBuffer", "CellType", "CellValue", "Mask", "MaskedCellBuffer", "NoData", "NarrowingError",
+__all__ = ["CellBuffer", "CellType", "CellValue", "Mask", "MaskedCellBuffer", "NoData", "Statistics", "NarrowingError",
            "NoDeviceError", "EcError", "ParseError", "build", "lib", "lazy", "ADD", "SUB", "MUL", "DIV"]

@@ -23,6 +23,14 @@ class Value(C.Structure):
     _fields_ = [("ct", C.c_uint8), ("pad", C.c_uint8 * 7), ("bits", C.c_uint64)]
 
 
+class Statistics(C.Structure):
+    """ec_statistics (extension: the reference has no statistics beyond min_max / counts)."""
+    _fields_ = [("count", C.c_uint64), ("min", Value), ("max", Value), ("mean", C.c_double), ("stddev", C.c_double)]
+
+
+MOMENT_WORDS = 9
+
+
 class DeviceInfo(C.Structure):
     _fields_ = [("device", C.c_int), ("sm_count", C.c_int), ("cc_major", C.c_int), ("cc_minor", C.c_int),
                 ("l2_bytes", C.c_size_t), ("total_mem_bytes", C.c_size_t), ("name", C.c_char * 128)]
@@ -132,6 +140,10 @@ def _signatures():
         "ec_buf_convert": (S, [VP, U8, PVP]),
         "ec_buf_min_max": (S, [VP, VP, PV, PV]),
         "ec_buf_cmp": (S, [VP, VP, PI]),
+        "ec_buf_statistics": (S, [VP, VP, C.POINTER(Statistics)]),
+        "ec_statistics_plan": (S, [PV, PV, PI, C.POINTER(C.c_double), PI]),
+        "ec_buf_moments": (S, [VP, VP, C.c_double, I, C.POINTER(U64)]),
+        "ec_statistics_finish": (S, [C.POINTER(U64), C.c_size_t, PV, PV, C.POINTER(Statistics)]),
         "ec_buf_normalized_difference": (S, [VP, VP, PVP]),
         "ec_buf_binary_scalar": (S, [I, VP, VP, I, PV, PVP]),
         "ec_mask_from_bools": (S, [VP, SZ, PVP]),

@@ -223,6 +223,25 @@ def _host(a, ct=None) -> np.ndarray:
     return a
 
 
+class Statistics:
+    """count / min / max / mean / population stddev of the valid cells (extension; ec_statistics)."""
+    __slots__ = ("count", "min", "max", "mean", "stddev")
+
+    def __init__(self, raw: "_lib.Statistics"):
+        self.count = int(raw.count)
+        self.min, self.max = CellValue._wrap(raw.min), CellValue._wrap(raw.max)
+        self.mean, self.stddev = float(raw.mean), float(raw.stddev)
+
+    def __repr__(self):
+        return f"Statistics(count={self.count}, min={self.min}, max={self.max}, mean={self.mean}, stddev={self.stddev})"
+
+
+def _statistics(buf_h, mask_h) -> Statistics:
+    raw = _lib.Statistics()
+    check(lib().ec_buf_statistics(buf_h, mask_h, C.byref(raw)))
+    return Statistics(raw)
+
+
 class CellBuffer:
     __slots__ = ("_h", "_keep")
 
@@ -339,6 +358,10 @@ class CellBuffer:
         mn, mx = Value(), Value()
         check(lib().ec_buf_min_max(self._h, None, C.byref(mn), C.byref(mx)))
         return CellValue._wrap(mn), CellValue._wrap(mx)
+
+    def statistics(self) -> "Statistics":
+        """count / min / max / mean / population stddev — an extension (the reference stops at min_max)."""
+        return _statistics(self._h, None)
 
     def to_vec(self, cell_type: CellType | None = None, out: np.ndarray | None = None) -> np.ndarray:
         """to_vec::<T>() (src/buffer.rs:175-185): convert on the device, then one D2H copy."""
@@ -652,6 +675,10 @@ class MaskedCellBuffer:
         mn, mx = Value(), Value()
         check(lib().ec_buf_min_max(self._buf._h, self._mask._h, C.byref(mn), C.byref(mx)))
         return CellValue._wrap(mn), CellValue._wrap(mx)
+
+    def statistics(self) -> "Statistics":
+        """statistics of the valid cells (extension, see CellBuffer.statistics)"""
+        return _statistics(self._buf._h, self._mask._h)
 
     def to_vec(self, cell_type=None):
         return self._buf.to_vec(cell_type)

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <limits>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -1220,6 +1221,119 @@ ec_status ec_buf_min_max(const ec_buf* b, const ec_mask* m, ec_value* mn, ec_val
     *mn = tagged<uint64_t>(b->ct, key_to_bits(b->ct, k[0]));
     *mx = tagged<uint64_t>(b->ct, key_to_bits(b->ct, k[1]));
     return EC_OK;
+}
+// ---- statistics extension (no reference counterpart): definition in ec_stats.cuh / DESIGN.md §4.6 ----
+ec_status ec_statistics_plan(const ec_value* mn, const ec_value* mx, int* kind, double* pivot, int* exp2) {
+    if (!ct_ok(mn->ct) || mn->ct != mx->ct) return invalid("ec_statistics_plan: min and max must share one cell type");
+    *pivot = 0.0;
+    *exp2 = 0;
+    if (value_cmp(*mn, *mx) > 0) { *kind = EC_STATS_EMPTY; return EC_OK; }  // the (T::MAX, T::MIN) seeds survived
+    const double lo = value_as_f64(*mn), hi = value_as_f64(*mx);
+    if (!std::isfinite(lo) || !std::isfinite(hi)) { *kind = EC_STATS_NONFINITE; return EC_OK; }
+    const volatile double half_lo = lo * 0.5, half_hi = hi * 0.5;  // one rounding per step, as the oracle states it
+    const double p = half_lo + half_hi;
+    const double up = hi - p, down = p - lo;
+    const double d = up > down ? up : down;
+    int e = 0;
+    if (d != 0) (void)std::frexp(d, &e);
+    *kind = EC_STATS_REGULAR;
+    *pivot = p;
+    *exp2 = e < -1000 ? -1000 : (e > 1024 ? 1024 : e);
+    return EC_OK;
+}
+// 8/16-bit cells: {count, A = sum x, B = sum x^2} (integer kernel) -> the window sums of the definition. With
+// s = 2 * pivot (an integer for a pivot from ec_statistics_plan) and Y = 2x - s:  y = Y/2 exactly,
+//   sum X1 = 2^(47-E) * sum y   = (2A - count*s)            << (46 - E)
+//   sum Z1 = 2^(47-2E) * sum y^2 = (4B - 4sA + count*s^2)   << (45 - 2E)      and both second windows are zero.
+static void moments_from_integer_sums(const uint64_t* in, int64_t s, int exp2, uint64_t* raw) {
+    const __int128 cnt = static_cast<__int128>(in[0]);
+    const __int128 A = static_cast<__int128>((static_cast<unsigned __int128>(in[2]) << 64) | in[1]);
+    const __int128 B = static_cast<__int128>((static_cast<unsigned __int128>(in[4]) << 64) | in[3]);
+    const unsigned __int128 x1 = static_cast<unsigned __int128>(2 * A - cnt * s) << (46 - exp2);
+    const unsigned __int128 z1 = static_cast<unsigned __int128>(4 * B - 4 * s * A + cnt * s * s) << (45 - 2 * exp2);
+    memset(raw, 0, EC_MOMENT_WORDS * sizeof(uint64_t));
+    raw[0] = in[0];
+    raw[1] = static_cast<uint64_t>(x1); raw[2] = static_cast<uint64_t>(x1 >> 64);
+    raw[5] = static_cast<uint64_t>(z1); raw[6] = static_cast<uint64_t>(z1 >> 64);
+}
+ec_status ec_buf_moments(const ec_buf* b, const ec_mask* m, double pivot, int exp2, uint64_t* raw) {
+    EC_TRY(ensure());
+    if (m && m->len != b->len) { set_error("Mask and buffer must have the same length."); return EC_LEN_MISMATCH; }
+    if (exp2 < -1000 || exp2 > 1024) return invalid("ec_buf_moments: exp2 out of range");
+    memset(raw, 0, EC_MOMENT_WORDS * sizeof(uint64_t));
+    if (b->len == 0) return EC_OK;
+    EC_TRY(resolve(b));
+    Scratch acc;
+    EC_TRY(acc.alloc(EC_MOMENT_WORDS * sizeof(uint64_t)));
+    EC_CUDA_TRY(cudaMemsetAsync(acc.p, 0, EC_MOMENT_WORDS * sizeof(uint64_t), cur_stream()), "cudaMemsetAsync");
+    // the integer route needs what a plan over 8/16-bit cells always gives: 2 * pivot integral and small, 0 <= E <= 17
+    const double twice = pivot * 2.0;
+    const bool integer_route = kSize[b->ct] <= 2 && exp2 >= 0 && exp2 <= 17 && std::fabs(twice) <= 131072.0 && twice == std::nearbyint(twice);
+    if (integer_route)
+        EC_LAUNCH(launch_int_moments(launch_ctx(), b->ct, rd(b), m ? m->words : nullptr, b->len, static_cast<unsigned long long*>(acc.p)), "int_moments");
+    else
+        EC_LAUNCH(launch_moments(launch_ctx(), b->ct, rd(b), m ? m->words : nullptr, b->len, pivot, std::ldexp(1.0, -exp2),
+                                 static_cast<unsigned long long*>(acc.p)), "moments");
+    uint64_t words[EC_MOMENT_WORDS];
+    EC_CUDA_TRY(cudaMemcpyAsync(words, acc.p, sizeof words, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
+    EC_TRY(sync_stream());
+    if (integer_route) moments_from_integer_sums(words, static_cast<int64_t>(twice), exp2, raw);
+    else memcpy(raw, words, sizeof words);
+    return EC_OK;
+}
+ec_status ec_statistics_finish(const uint64_t* raws, size_t n_parts, const ec_value* mn, const ec_value* mx, ec_statistics* out) {
+    int kind, e;
+    double p;
+    EC_TRY(ec_statistics_plan(mn, mx, &kind, &p, &e));
+    unsigned __int128 tot[4] = {0, 0, 0, 0};  // two's complement, modulo 2^128
+    uint64_t count = 0;
+    for (size_t i = 0; i < n_parts; ++i) {
+        const uint64_t* r = raws + i * EC_MOMENT_WORDS;
+        count += r[0];
+        for (int k = 0; k < 4; ++k) tot[k] += (static_cast<unsigned __int128>(r[2 + 2 * k]) << 64) | r[1 + 2 * k];
+    }
+    const double qnan = std::numeric_limits<double>::quiet_NaN();
+    out->count = count;
+    out->min = *mn;
+    out->max = *mx;
+    out->mean = out->stddev = qnan;
+    if (kind == EC_STATS_EMPTY || count == 0) return EC_OK;
+    if (kind == EC_STATS_NONFINITE) {
+        const double lo = value_as_f64(*mn), hi = value_as_f64(*mx);
+        if (!std::isnan(lo) && !std::isnan(hi) && !(std::isinf(lo) && std::isinf(hi))) out->mean = std::isinf(lo) ? lo : hi;
+        return EC_OK;
+    }
+    // one rounding per operation (host code is built with -ffp-contract=off)
+    volatile double f[4];
+    for (int k = 0; k < 4; ++k) f[k] = static_cast<double>(static_cast<__int128>(tot[k]));
+    const volatile double s1 = std::ldexp(f[0], -47) + std::ldexp(f[1], -95);
+    const volatile double s2 = std::ldexp(f[2], -47) + std::ldexp(f[3], -95);
+    const double n = static_cast<double>(count);
+    const volatile double m1 = s1 / n, m2 = s2 / n;
+    const volatile double sq = m1 * m1;
+    double var = m2 - sq;
+    if (var < 0) var = 0.0;
+    out->mean = p + std::ldexp(m1, e);
+    out->stddev = std::ldexp(std::sqrt(var), e);
+    return EC_OK;
+}
+ec_status ec_buf_statistics(const ec_buf* b, const ec_mask* m, ec_statistics* out) {
+    ec_value mn, mx;
+    EC_TRY(ec_buf_min_max(b, m, &mn, &mx));
+    int kind, e;
+    double p;
+    EC_TRY(ec_statistics_plan(&mn, &mx, &kind, &p, &e));
+    uint64_t raw[EC_MOMENT_WORDS] = {0};
+    if (kind == EC_STATS_REGULAR) {
+        EC_TRY(ec_buf_moments(b, m, p, e, raw));
+    } else if (m) {  // nothing to sum, but the count of valid cells is still reported
+        size_t d, nd;
+        EC_TRY(ec_mask_counts(m, &d, &nd));
+        raw[0] = d;
+    } else {
+        raw[0] = b->len;
+    }
+    return ec_statistics_finish(raw, 1, &mn, &mx, out);
 }
 ec_status ec_buf_cmp(const ec_buf* l, const ec_buf* r, int* ordering) {
     EC_TRY(ensure());

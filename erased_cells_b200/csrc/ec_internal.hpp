@@ -83,6 +83,10 @@ cudaError_t launch_min_max(const Launch& L, int ct, const void* a, const uint32_
 cudaError_t launch_popcount(const Launch& L, const uint32_t* words, size_t nwords, const ReduceScratch& s, uint64_t second_word);
 ec_status reduce_min_max_peer(const ec_buf* b, const ec_mask* m, const PeerExchange& px, uint64_t* k0, uint64_t* k1);
 ec_status reduce_popcount_peer(const ec_mask* m, const PeerExchange& px, uint64_t* ones, uint64_t* len_sum);
+// statistics extension: exact fixed-point moment sums into acc[9] (zeroed by the caller), see ec_stats.cuh
+cudaError_t launch_moments(const Launch& L, int ct, const void* a, const uint32_t* mask, size_t n, double pivot, double scale,
+                           unsigned long long* acc);
+cudaError_t launch_int_moments(const Launch& L, int ct, const void* a, const uint32_t* mask, size_t n, unsigned long long* acc);
 cudaError_t launch_first_diff(const Launch& L, int cell_bytes, const void* a, const void* b, size_t n,
                               const ReduceScratch& s);
 // masks

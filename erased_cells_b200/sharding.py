@@ -13,8 +13,11 @@ import ctypes as C
 
 import numpy as np
 
+from . import _lib
 from ._lib import Value, check, lib
-from .api import CellBuffer, CellType, CellValue, Mask
+from .api import CellBuffer, CellType, CellValue, Mask, Statistics
+
+ST_REGULAR, ST_EMPTY, ST_NONFINITE = range(3)
 
 
 def row_strip(width: int, height: int, n_shards: int, shard: int) -> tuple[int, int]:
@@ -61,6 +64,59 @@ def counts_sharded(mask: Mask, group=None) -> tuple[int, int]:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return int(t[0]), int(t[1])
+
+
+# ---- statistics of a sharded raster (extension; definition in DESIGN.md §4.6) ------------------------------------
+# global min/max (one all-reduce) -> the same (pivot, exponent) on every rank -> per-strip exact integer moment sums
+# (one device pass) -> all-gather of 72 bytes per rank -> the same host finish everywhere. Exact sums make the result
+# independent of the number of strips.
+def statistics_plan(mn: CellValue, mx: CellValue) -> tuple[int, float, int]:
+    kind, pivot, exp2 = C.c_int(), C.c_double(), C.c_int()
+    check(lib().ec_statistics_plan(C.byref(mn._v), C.byref(mx._v), C.byref(kind), C.byref(pivot), C.byref(exp2)))
+    return kind.value, pivot.value, exp2.value
+
+
+def moments(shard: CellBuffer, mask: Mask | None, pivot: float, exp2: int) -> np.ndarray:
+    """this strip's raw accumulators: uint64[9] = {count, four 128-bit two's complement sums}"""
+    raw = np.zeros(_lib.MOMENT_WORDS, dtype=np.uint64)
+    check(lib().ec_buf_moments(shard._h, mask._h if mask is not None else None, pivot, exp2,
+                               raw.ctypes.data_as(C.POINTER(C.c_uint64))))
+    return raw
+
+
+def finish_statistics(raws, mn: CellValue, mx: CellValue) -> Statistics:
+    raws = np.ascontiguousarray(np.asarray(raws, dtype=np.uint64).reshape(-1, _lib.MOMENT_WORDS))
+    out = _lib.Statistics()
+    check(lib().ec_statistics_finish(raws.ctypes.data_as(C.POINTER(C.c_uint64)), raws.shape[0], C.byref(mn._v),
+                                     C.byref(mx._v), C.byref(out)))
+    return Statistics(out)
+
+
+def gather_statistics(raw: np.ndarray, mn: CellValue, mx: CellValue, group=None) -> Statistics:
+    """all-gather every rank's raw accumulators and finish (every rank gets the same result)"""
+    import torch
+    import torch.distributed as dist
+    parts = raw.reshape(1, -1)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        t = torch.from_numpy(raw.view(np.int64).copy())
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda()
+        got = [torch.empty_like(t) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(got, t, group=group)
+        parts = np.stack([g.cpu().numpy().view(np.uint64) for g in got])
+    return finish_statistics(parts, mn, mx)
+
+
+def statistics_sharded(shard: CellBuffer, mask: Mask | None = None, group=None, comm: "Comm | None" = None) -> Statistics:
+    """statistics of the whole raster from this rank's strip; `comm` finishes min/max inside the reduction kernel"""
+    mn, mx = comm.min_max(shard, mask) if comm is not None else min_max_sharded(shard, mask, group)
+    kind, pivot, exp2 = statistics_plan(mn, mx)
+    if kind == ST_REGULAR:
+        raw = moments(shard, mask, pivot, exp2)
+    else:
+        raw = np.zeros(_lib.MOMENT_WORDS, dtype=np.uint64)
+        raw[0] = mask.counts()[0] if mask is not None else shard.len()
+    return gather_statistics(raw, mn, mx, group)
 
 
 class Comm:
@@ -149,6 +205,9 @@ class ShardedCellBuffer:
     def min_max(self):
         return self.comm.min_max(self.strip)
 
+    def statistics(self, group=None) -> Statistics:
+        return statistics_sharded(self.strip, None, group, self.comm)
+
     def gather(self) -> np.ndarray:
         """The whole raster on every rank's host (tests / small rasters)."""
         import torch.distributed as dist
@@ -185,3 +244,6 @@ class ShardedMaskedCellBuffer:
 
     def counts(self):
         return self.comm.counts(self.strip.mask())
+
+    def statistics(self, group=None) -> Statistics:
+        return statistics_sharded(self.strip.buffer(), self.strip.mask(), group, self.comm)

@@ -77,6 +77,18 @@ typedef struct ec_value {
     uint64_t bits;
 } ec_value;
 
+/* Statistics of the valid cells — an EXTENSION, the reference has none beyond min_max and Mask::counts (its only
+ * mention is a comment quoting gdal_calc.py, src/gdal/rasterband.rs:152-156). mean / stddev (population, as GDAL's
+ * STATISTICS_STDDEV) follow the order-independent definition of DESIGN.md §4.6: bit-identical for any grid and any
+ * number of GPUs; within 2 ULP of the exactly rounded value on the data of tests/test_oracle_self.py. */
+typedef struct ec_statistics {
+    uint64_t count;      /* valid cells */
+    ec_value min, max;   /* as ec_buf_min_max: total order, (T::MAX, T::MIN) when count == 0 */
+    double mean, stddev; /* canonical NaN when count == 0 or a valid cell is NaN; mean = +-inf / stddev = NaN with infinities */
+} ec_statistics;
+enum { EC_STATS_REGULAR = 0, EC_STATS_EMPTY = 1, EC_STATS_NONFINITE = 2 };
+#define EC_MOMENT_WORDS 9 /* {count, X1.lo, X1.hi, X2.lo, X2.hi, Z1.lo, Z1.hi, Z2.lo, Z2.hi}: 128-bit two's complement sums */
+
 typedef struct ec_buf ec_buf;   /* CellBuffer: typed cells in HBM */
 typedef struct ec_mask ec_mask; /* Mask: validity bits in HBM, packed 32 cells per little-endian word */
 typedef struct ec_event ec_event;
@@ -188,6 +200,16 @@ ec_status ec_buf_convert(const ec_buf* b, uint8_t ct, ec_buf** out);
 ec_status ec_buf_min_max(const ec_buf* b, const ec_mask* mask_or_null, ec_value* min_out, ec_value* max_out);
 /* Ord/Eq for CellBuffer (:373-436): cell type, then lexicographic total order, then length */
 ec_status ec_buf_cmp(const ec_buf* l, const ec_buf* r, int* ordering);
+
+/* ---- statistics (extension, see ec_statistics above) ---------------------------------------------
+ * ec_buf_statistics = min_max pass + one moments pass (skipped when empty or non-finite). The three pieces below
+ * are what a row-strip sharded caller composes: global min/max -> plan (host) -> per-strip moments (device, exact
+ * integer sums) -> finish over all strips' raw words (host). */
+ec_status ec_buf_statistics(const ec_buf* b, const ec_mask* mask_or_null, ec_statistics* out);
+ec_status ec_statistics_plan(const ec_value* min, const ec_value* max, int* kind, double* pivot, int* exp2);
+ec_status ec_buf_moments(const ec_buf* b, const ec_mask* mask_or_null, double pivot, int exp2, uint64_t raw[EC_MOMENT_WORDS]);
+ec_status ec_statistics_finish(const uint64_t* raws, size_t n_parts, const ec_value* min, const ec_value* max,
+                               ec_statistics* out);
 
 /* ---- fused op chains behind the same operators -------------------------
  * ec_set_lazy(1) (per thread, default 0): ec_buf_binary / ec_buf_scalar / ec_masked_binary return at once with a

@@ -404,3 +404,103 @@ def tight_min_max(a, mask=None):
     m = _m(mask) if mask is not None else None
     lib().eco_tight_min_max(ct_of(a), _p(a), len(a), _p(m) if m is not None else None, C.byref(mn), C.byref(mx))
     return mn, mx
+
+
+# ---------------------------------------------------------------------------------------------
+# EXTENSION — statistics (count / min / max / mean / population stddev).
+# The reference has NO statistics beyond min_max and Mask::counts (STATISTICS_MEAN /
+# STATISTICS_STDDEV occur only in a comment quoting gdal_calc.py output, src/gdal/rasterband.rs:152-156), so
+# there is nothing to pin against: PARITY UNPINNED. What is restated here is this repo's own DEFINITION
+# (DESIGN.md §4.6), chosen so that the result is a function of the multiset of valid cells only — independent
+# of summation order, grid size and the number of GPUs:
+#   1. (mn, mx) = min_max of the valid cells; x = to_f64(cell)
+#   2. pivot p = fl(xmin/2 + xmax/2); E = binary exponent with max|x - p| < 2^E (clamped to [-1000, 1024])
+#   3. per valid cell: y = fl(fl(x - p) * 2^-E), z = fl(y * y); each is split into two 48-bit fixed-point
+#      windows (units 2^-47 and 2^-95, round-to-nearest-even at the second), summed EXACTLY as integers
+#   4. S1, S2 -> m1 = S1/n, m2 = S2/n, var = max(m2 - m1*m1, 0); mean = p + m1*2^E; stddev = sqrt(var)*2^E
+# numpy float64 arithmetic below is IEEE binary64 with one rounding per operation, like the device code
+# (__dadd_rn/__dmul_rn) and the host finish.
+_C1 = 48.0                      # 1.5 * 2^5: ulp = 2^-47
+_C2 = 48.0 * 2.0 ** -48         # ulp = 2^-95
+_K1 = int(np.float64(_C1).view(np.int64))
+_K2 = int(np.float64(_C2).view(np.int64))
+_QNAN = float(np.uint64(0x7FF8000000000000).view(np.float64))
+ST_REGULAR, ST_EMPTY, ST_NONFINITE = range(3)
+
+
+def _value_f64(v: Value) -> float:
+    return float(v.numpy().astype(np.float64)) if v.ct != Float64 else float(v.numpy())
+
+
+def statistics_plan(mn: Value, mx: Value):
+    """(kind, pivot, exp2) from the min/max of the valid cells."""
+    if value_cmp(mn, mx) > 0:  # the (T::MAX, T::MIN) seeds survived: no valid cell
+        return ST_EMPTY, 0.0, 0
+    lo, hi = np.float64(_value_f64(mn)), np.float64(_value_f64(mx))
+    if not (np.isfinite(lo) and np.isfinite(hi)):
+        return ST_NONFINITE, 0.0, 0
+    p = np.float64(lo * np.float64(0.5)) + np.float64(hi * np.float64(0.5))
+    d = max(np.float64(hi - p), np.float64(p - lo))
+    e = 0 if d == 0 else int(np.frexp(d)[1])
+    return ST_REGULAR, float(p), max(-1000, min(1024, e))
+
+
+def _windows(v: np.ndarray):
+    t1 = v + np.float64(_C1)
+    x1 = t1.view(np.int64) - np.int64(_K1)
+    r = v - (t1 - np.float64(_C1))
+    t2 = r + np.float64(_C2)
+    x2 = t2.view(np.int64) - np.int64(_K2)
+    return x1, x2
+
+
+def _isum(x: np.ndarray) -> int:
+    """exact integer sum of int64 terms below 2^48 in magnitude"""
+    return sum(int(x[i:i + (1 << 14)].sum(dtype=np.int64)) for i in range(0, len(x), 1 << 14))
+
+
+def moments_raw(a, mask, pivot: float, exp2: int):
+    """[count, sum X1, sum X2, sum Z1, sum Z2] as python ints."""
+    a = _c(a)
+    if mask is not None:
+        a = a[np.ascontiguousarray(mask, dtype=bool)]
+    with np.errstate(all="ignore"):
+        y = (a.astype(np.float64) - np.float64(pivot)) * np.float64(np.ldexp(1.0, -exp2))
+        x1, x2 = _windows(y)
+        z1, z2 = _windows(y * y)
+    return [len(a), _isum(x1), _isum(x2), _isum(z1), _isum(z2)]
+
+
+def statistics_finish(raws, mn: Value, mx: Value):
+    """combine per-shard raw accumulators -> dict(count, min, max, mean, stddev)"""
+    import math
+    kind, p, e = statistics_plan(mn, mx)
+    tot = [sum(r[i] for r in raws) for i in range(5)]
+    out = dict(count=tot[0], min=mn, max=mx, mean=_QNAN, stddev=_QNAN)
+    if kind == ST_EMPTY or tot[0] == 0:
+        return out
+    if kind == ST_NONFINITE:
+        lo, hi = _value_f64(mn), _value_f64(mx)
+        if not (math.isnan(lo) or math.isnan(hi)) and not (lo == -math.inf and hi == math.inf):
+            out["mean"] = lo if lo == -math.inf else hi
+        return out
+    n = float(tot[0])
+    s1 = math.ldexp(float(tot[1]), -47) + math.ldexp(float(tot[2]), -95)
+    s2 = math.ldexp(float(tot[3]), -47) + math.ldexp(float(tot[4]), -95)
+    m1, m2 = s1 / n, s2 / n
+    var = m2 - m1 * m1
+    if var < 0:
+        var = 0.0
+    out["mean"] = p + math.ldexp(m1, e)
+    out["stddev"] = math.ldexp(math.sqrt(var), e)
+    return out
+
+
+def statistics(a, mask=None):
+    mn, mx = min_max(a, mask)
+    kind, p, e = statistics_plan(mn, mx)
+    if kind == ST_REGULAR:
+        raw = moments_raw(a, mask, p, e)
+    else:
+        raw = [int(len(a) if mask is None else np.count_nonzero(mask)), 0, 0, 0, 0]
+    return statistics_finish([raw], mn, mx)

@@ -42,6 +42,28 @@ def _worker(rank, world, port, q):
         a, b = sharding.finish_min_max(ct, k2)
         r0 = orc.tight_min_max(full[: sharding.row_strip(width, height, world, 0)[1]])
         ok &= (a.bits, b.bits) == (r0[0].bits, r0[1].bits)
+    # statistics (extension): global min/max -> shared plan -> per-strip exact sums -> all-gather -> finish
+    for ct in CellType:
+        full = synth.host(ct, width * height, 0xEC70 + int(ct), kind=synth.REAL_RANGE, lo=-300.0 if ct.is_signed() else 3.0, hi=120.0)
+        valid = synth.host(CellType.UInt8, width * height, 0xEC7F) < 200
+        off, ln = sharding.row_strip(width, height, world, rank)
+        strip, vstrip = full[off:off + ln], valid[off:off + ln]
+        mn, mx = orc.tight_min_max(strip, vstrip)
+        keys = torch.from_numpy(sharding.keys_of(CellValue(ct, mn.numpy()), CellValue(ct, mx.numpy())))
+        gmn, gmx = sharding.finish_min_max(ct, keys)
+        kind, pivot, exp2 = sharding.statistics_plan(gmn, gmx)
+        ok &= kind == sharding.ST_REGULAR
+        raw = orc.moments_raw(strip, vstrip, pivot, exp2)
+        words = np.zeros(9, dtype=np.uint64)
+        words[0] = raw[0]
+        for k in range(4):
+            v = raw[1 + k] & ((1 << 128) - 1)
+            words[1 + 2 * k], words[2 + 2 * k] = v & (2 ** 64 - 1), v >> 64
+        got = sharding.gather_statistics(words, gmn, gmx)
+        want = orc.statistics(full, valid)
+        ok &= got.count == want["count"]
+        ok &= (np.float64(got.mean).view(np.uint64), np.float64(got.stddev).view(np.uint64)) == \
+              (np.float64(want["mean"]).view(np.uint64), np.float64(want["stddev"]).view(np.uint64))
     # strips tile the raster exactly
     lens = [sharding.row_strip(width, height, world, g) for g in range(world)]
     ok &= sum(l for _, l in lens) == width * height and all(lens[g][0] + lens[g][1] == lens[g + 1][0] for g in range(world - 1))
