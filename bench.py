@@ -489,6 +489,9 @@ def other_configs(ec, L, torch, dist, rank, world, barrier, max_over_ranks, peak
     rs = r * 0.0001
     c3["masked_min_max_f64"] = entry(timed(lambda: rs.min_max()), 8.125 * n3, n3, note="includes the 16-byte D2H + stream sync of the result")
     c3["counts"] = entry(timed(lambda: rs.counts()), 0.125 * n3, n3)
+    # statistics extension (count/min/max/mean/stddev; the reference has none): integer cells of <= 32 bits are ONE pass
+    c3["statistics_masked_i16_one_pass"] = entry(timed(lambda: ma.statistics()), 2.125 * n3, n3, note="extension: min, max, count, sum x, sum x^2 in one read; host finish + sync included")
+    c3["statistics_masked_f64_two_passes"] = entry(timed(lambda: rs.statistics()), 8.125 * n3, n3, note="extension: min_max pass + FP64 window moments pass; bytes counted once")
     res["c3_masked_i16_16384"] = c3
     del a, b, ma, mb, r, rs
 
@@ -519,7 +522,14 @@ def other_configs(ec, L, torch, dist, rank, world, barrier, max_over_ranks, peak
         res["c4_f32_32768_min_max_sharded_fused"] = entry(timed(lambda: comm.min_max(strip), 10), 4.0 * n4, n4, scaling="strong", shards=world,
                                                           peer_exchange=comm.peer_exchange, result_bits=[hex(got[0].bits), hex(got[1].bits)],
                                                           note="ec_buf_min_max_sharded: one kernel per GPU when peer_exchange is true, else kernel + NCCL")
+        st = sharding.statistics_sharded(strip, None, None, comm)
+        res["c4_f32_32768_statistics_sharded"] = entry(timed(lambda: sharding.statistics_sharded(strip, None, None, comm), 5), 4.0 * n4, n4, scaling="strong", shards=world,
+                                                       result=[st.count, st.mean, st.stddev], note="extension: fused sharded min_max, FP64 moments pass per strip, all-gather of 72 B, host finish")
         comm.close()
+    else:
+        st = strip.statistics()
+        res["c4_f32_32768_statistics"] = entry(timed(lambda: strip.statistics(), 5), 4.0 * n4, n4, result=[st.count, st.mean, st.stddev],
+                                               note="extension: min_max pass + FP64 window moments pass (FP64-issue-bound for f32); bytes counted once")
     del strip
 
     # config 5: NDVI (nir - red) / (nir + red), u16 32768^2 -> f64, one tile per GPU (weak)

@@ -1241,20 +1241,18 @@ ec_status ec_statistics_plan(const ec_value* mn, const ec_value* mx, int* kind, 
     *exp2 = e < -1000 ? -1000 : (e > 1024 ? 1024 : e);
     return EC_OK;
 }
-// 8/16-bit cells: {count, A = sum x, B = sum x^2} (integer kernel) -> the window sums of the definition. With
-// s = 2 * pivot (an integer for a pivot from ec_statistics_plan) and Y = 2x - s:  y = Y/2 exactly,
-//   sum X1 = 2^(47-E) * sum y   = (2A - count*s)            << (46 - E)
-//   sum Z1 = 2^(47-2E) * sum y^2 = (4B - 4sA + count*s^2)   << (45 - 2E)      and both second windows are zero.
-static void moments_from_integer_sums(const uint64_t* in, int64_t s, int exp2, uint64_t* raw) {
-    const __int128 cnt = static_cast<__int128>(in[0]);
-    const __int128 A = static_cast<__int128>((static_cast<unsigned __int128>(in[2]) << 64) | in[1]);
-    const __int128 B = static_cast<__int128>((static_cast<unsigned __int128>(in[4]) << 64) | in[3]);
-    const unsigned __int128 x1 = static_cast<unsigned __int128>(2 * A - cnt * s) << (46 - exp2);
-    const unsigned __int128 z1 = static_cast<unsigned __int128>(4 * B - 4 * s * A + cnt * s * s) << (45 - 2 * exp2);
-    memset(raw, 0, EC_MOMENT_WORDS * sizeof(uint64_t));
-    raw[0] = in[0];
-    raw[1] = static_cast<uint64_t>(x1); raw[2] = static_cast<uint64_t>(x1 >> 64);
-    raw[5] = static_cast<uint64_t>(z1); raw[6] = static_cast<uint64_t>(z1 >> 64);
+// Integer cells of at most 32 bits take the exact integer route: raw = {count, A = sum x, B = sum x^2, 0, 0}
+// (pivot-free), everything else the FP64 window route: raw = {count, X1, X2, Z1, Z2}.
+static inline bool stats_integer_route(uint8_t ct) { return ct_integral(ct) && kSize[ct] <= 4; }
+static const uint64_t kIntStatsInit[8] = {0, 0, 0, 0, 0, 0xFFFFFFFFull, 0, 0};
+static ec_status run_int_stats(const ec_buf* b, const ec_mask* m, uint64_t* w /*[8]*/) {
+    EC_TRY(resolve(b));
+    Scratch acc;
+    EC_TRY(acc.alloc(sizeof kIntStatsInit));
+    EC_CUDA_TRY(cudaMemcpyAsync(acc.p, kIntStatsInit, sizeof kIntStatsInit, cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
+    EC_LAUNCH(launch_int_stats(launch_ctx(), b->ct, rd(b), m ? m->words : nullptr, b->len, static_cast<unsigned long long*>(acc.p)), "int_stats");
+    EC_CUDA_TRY(cudaMemcpyAsync(w, acc.p, sizeof kIntStatsInit, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
+    return sync_stream();
 }
 ec_status ec_buf_moments(const ec_buf* b, const ec_mask* m, double pivot, int exp2, uint64_t* raw) {
     EC_TRY(ensure());
@@ -1262,24 +1260,20 @@ ec_status ec_buf_moments(const ec_buf* b, const ec_mask* m, double pivot, int ex
     if (exp2 < -1000 || exp2 > 1024) return invalid("ec_buf_moments: exp2 out of range");
     memset(raw, 0, EC_MOMENT_WORDS * sizeof(uint64_t));
     if (b->len == 0) return EC_OK;
+    if (stats_integer_route(b->ct)) {
+        uint64_t w[8];
+        EC_TRY(run_int_stats(b, m, w));
+        memcpy(raw, w, 5 * sizeof(uint64_t));
+        return EC_OK;
+    }
     EC_TRY(resolve(b));
     Scratch acc;
     EC_TRY(acc.alloc(EC_MOMENT_WORDS * sizeof(uint64_t)));
     EC_CUDA_TRY(cudaMemsetAsync(acc.p, 0, EC_MOMENT_WORDS * sizeof(uint64_t), cur_stream()), "cudaMemsetAsync");
-    // the integer route needs what a plan over 8/16-bit cells always gives: 2 * pivot integral and small, 0 <= E <= 17
-    const double twice = pivot * 2.0;
-    const bool integer_route = kSize[b->ct] <= 2 && exp2 >= 0 && exp2 <= 17 && std::fabs(twice) <= 131072.0 && twice == std::nearbyint(twice);
-    if (integer_route)
-        EC_LAUNCH(launch_int_moments(launch_ctx(), b->ct, rd(b), m ? m->words : nullptr, b->len, static_cast<unsigned long long*>(acc.p)), "int_moments");
-    else
-        EC_LAUNCH(launch_moments(launch_ctx(), b->ct, rd(b), m ? m->words : nullptr, b->len, pivot, std::ldexp(1.0, -exp2),
-                                 static_cast<unsigned long long*>(acc.p)), "moments");
-    uint64_t words[EC_MOMENT_WORDS];
-    EC_CUDA_TRY(cudaMemcpyAsync(words, acc.p, sizeof words, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
-    EC_TRY(sync_stream());
-    if (integer_route) moments_from_integer_sums(words, static_cast<int64_t>(twice), exp2, raw);
-    else memcpy(raw, words, sizeof words);
-    return EC_OK;
+    EC_LAUNCH(launch_moments(launch_ctx(), b->ct, rd(b), m ? m->words : nullptr, b->len, pivot, std::ldexp(1.0, -exp2),
+                             static_cast<unsigned long long*>(acc.p)), "moments");
+    EC_CUDA_TRY(cudaMemcpyAsync(raw, acc.p, EC_MOMENT_WORDS * sizeof(uint64_t), cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
+    return sync_stream();
 }
 ec_status ec_statistics_finish(const uint64_t* raws, size_t n_parts, const ec_value* mn, const ec_value* mx, ec_statistics* out) {
     int kind, e;
@@ -1303,11 +1297,21 @@ ec_status ec_statistics_finish(const uint64_t* raws, size_t n_parts, const ec_va
         if (!std::isnan(lo) && !std::isnan(hi) && !(std::isinf(lo) && std::isinf(hi))) out->mean = std::isinf(lo) ? lo : hi;
         return EC_OK;
     }
-    // one rounding per operation (host code is built with -ffp-contract=off)
-    volatile double f[4];
-    for (int k = 0; k < 4; ++k) f[k] = static_cast<double>(static_cast<__int128>(tot[k]));
-    const volatile double s1 = std::ldexp(f[0], -47) + std::ldexp(f[1], -95);
-    const volatile double s2 = std::ldexp(f[2], -47) + std::ldexp(f[3], -95);
+    // one rounding per operation (host code is built with -ffp-contract=off; int128 -> double is round-to-nearest-even)
+    volatile double s1, s2;
+    if (stats_integer_route(mn->ct)) {
+        // y = x - pivot = Y/2 with Y = 2x - s, s = 2 * pivot = min + max (an integer): the sums of y' = y * 2^-E and
+        // of y'^2 are exact rationals, rounded once
+        const __int128 cnt = static_cast<__int128>(count), A = static_cast<__int128>(tot[0]), B = static_cast<__int128>(tot[1]);
+        const __int128 s = static_cast<__int128>(p * 2.0);
+        s1 = std::ldexp(static_cast<double>(2 * A - cnt * s), -1 - e);
+        s2 = std::ldexp(static_cast<double>(4 * B - 4 * s * A + cnt * s * s), -2 - 2 * e);
+    } else {
+        volatile double f[4];
+        for (int k = 0; k < 4; ++k) f[k] = static_cast<double>(static_cast<__int128>(tot[k]));
+        s1 = std::ldexp(f[0], -47) + std::ldexp(f[1], -95);
+        s2 = std::ldexp(f[2], -47) + std::ldexp(f[3], -95);
+    }
     const double n = static_cast<double>(count);
     const volatile double m1 = s1 / n, m2 = s2 / n;
     const volatile double sq = m1 * m1;
@@ -1318,12 +1322,31 @@ ec_status ec_statistics_finish(const uint64_t* raws, size_t n_parts, const ec_va
     return EC_OK;
 }
 ec_status ec_buf_statistics(const ec_buf* b, const ec_mask* m, ec_statistics* out) {
+    EC_TRY(ensure());
+    if (m && m->len != b->len) { set_error("Mask and buffer must have the same length."); return EC_LEN_MISMATCH; }
     ec_value mn, mx;
+    uint64_t raw[EC_MOMENT_WORDS] = {0};
+    if (stats_integer_route(b->ct) && b->len) {
+        // one pass: min, max, count and both integer sums; the pivot is only needed by the finish
+        uint64_t w[8];
+        EC_TRY(run_int_stats(b, m, w));
+        memcpy(raw, w, 5 * sizeof(uint64_t));
+        if (w[0] == 0) {  // no valid cell: the seeds, as min_max reports them
+            uint64_t k[2];
+            key_seeds(b->ct, &k[0], &k[1]);
+            mn = tagged<uint64_t>(b->ct, key_to_bits(b->ct, k[0]));
+            mx = tagged<uint64_t>(b->ct, key_to_bits(b->ct, k[1]));
+        } else {
+            const uint64_t bias = ct_signed(b->ct) ? 1ull << (8 * kSize[b->ct] - 1) : 0ull;
+            mn = tagged<uint64_t>(b->ct, w[5] ^ bias);
+            mx = tagged<uint64_t>(b->ct, w[6] ^ bias);
+        }
+        return ec_statistics_finish(raw, 1, &mn, &mx, out);
+    }
     EC_TRY(ec_buf_min_max(b, m, &mn, &mx));
     int kind, e;
     double p;
     EC_TRY(ec_statistics_plan(&mn, &mx, &kind, &p, &e));
-    uint64_t raw[EC_MOMENT_WORDS] = {0};
     if (kind == EC_STATS_REGULAR) {
         EC_TRY(ec_buf_moments(b, m, p, e, raw));
     } else if (m) {  // nothing to sum, but the count of valid cells is still reported

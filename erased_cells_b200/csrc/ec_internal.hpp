@@ -86,7 +86,7 @@ ec_status reduce_popcount_peer(const ec_mask* m, const PeerExchange& px, uint64_
 // statistics extension: exact fixed-point moment sums into acc[9] (zeroed by the caller), see ec_stats.cuh
 cudaError_t launch_moments(const Launch& L, int ct, const void* a, const uint32_t* mask, size_t n, double pivot, double scale,
                            unsigned long long* acc);
-cudaError_t launch_int_moments(const Launch& L, int ct, const void* a, const uint32_t* mask, size_t n, unsigned long long* acc);
+cudaError_t launch_int_stats(const Launch& L, int ct, const void* a, const uint32_t* mask, size_t n, unsigned long long* acc);
 cudaError_t launch_first_diff(const Launch& L, int cell_bytes, const void* a, const void* b, size_t n,
                               const ReduceScratch& s);
 // masks

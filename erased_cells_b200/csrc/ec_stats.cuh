@@ -9,8 +9,9 @@
 //   mantissa bits, the remainder r = v - (t1 - 48) is exact, t2 = fl(r + 48 * 2^-48) carries rint(r * 2^95) — and
 //   the four integer streams are summed EXACTLY (128-bit two's complement).
 //
-// One streaming pass, algorithmic bytes per cell = size_of(T) (+ 1/8 with a mask); 12 FP64 operations per cell,
-// which is what bounds the narrow cell types (see the kernel table in DESIGN.md).
+// One streaming pass, algorithmic bytes per cell = size_of(T) (+ 1/8 with a mask); 12 FP64 operations per cell, which
+// is what bounds Float32 (64-bit cells stay HBM-bound). Integer cells of at most 32 bits never come here: for them
+// y is exact and the sums are exact integers, see int_stats_kernel below.
 #pragma once
 #include "ec_reduce.cuh"
 
@@ -142,25 +143,32 @@ __global__ void __launch_bounds__(THREADS) moments_kernel(const T* __restrict__ 
     }
 }
 
-// ---- 8/16-bit cells: the same raw sums from plain integer moments -------------------------------------------------
-// For these types every step of the definition is exact (y is a multiple of 1/2 below 2^16, y*y needs 34 bits), the
-// second windows are zero and the first ones are 2^(47-E) * sum(y) and 2^(47-2E) * sum(y^2). So the device only sums
-// x and x^2 over the valid cells — packed dot products for 8-bit cells, 16x16 multiplies for 16-bit ones, no FP64 at
-// all — and the host rewrites {count, A = sum x, B = sum x^2} into the window sums (ec_api.cu: moments_from_integer_sums).
-// acc[5] = {count, A.lo, A.hi, B.lo, B.hi}, 128-bit two's complement.
+// ---- integer cells of at most 32 bits: everything in ONE pass, no FP64 ---------------------------------------------
+// For these types y = x - pivot is exact, so the definition asks for the correctly rounded sums of y and y^2 — which
+// follow on the host from {count, A = sum x, B = sum x^2} (exact integers) once the pivot is known. The device
+// therefore needs no pivot: one read of the cells yields min, max, count, A and B, i.e. the whole ec_buf_statistics.
+// 8-bit cells use packed dot products, 16-bit ones 16x16 multiplies, 32-bit ones one wide multiply whose two halves
+// are summed separately (no carry chain); min/max run on biased unsigned values, two 16-bit lanes per register for
+// the narrow types (as min_max_kernel does); a masked-out cell is forced to zero / to the identity of min and max.
+// acc[7] = {count, A.lo, A.hi, B.lo, B.hi, min (biased, preset to all ones), max (biased, preset to 0)};
+// A and B are 128-bit two's complement, summed across CTAs with carry-tracking atomics.
 template <class T, bool MASKED, int VB, int UNROLL, int THREADS>
-__global__ void __launch_bounds__(THREADS) int_moments_kernel(const T* __restrict__ a, const uint32_t* __restrict__ m, size_t n,
-                                                              unsigned long long* __restrict__ acc) {
-    static_assert(sizeof(T) <= 2, "integer moments are for 8- and 16-bit cells");
+__global__ void __launch_bounds__(THREADS) int_stats_kernel(const T* __restrict__ a, const uint32_t* __restrict__ m, size_t n,
+                                                            unsigned long long* __restrict__ acc) {
+    static_assert(sizeof(T) <= 4 && std::is_integral<T>::value, "integer cells of at most 32 bits");
     constexpr bool SG = std::is_signed<T>::value;
-    constexpr int V = VB / sizeof(T);          // cells per 32-byte load
-    constexpr int W = VB / 4;                  // 32-bit words per load
-    constexpr int CPW = 4 / sizeof(T);         // cells per word
+    constexpr int V = VB / sizeof(T);
+    constexpr int W = VB / 4;
+    constexpr int CPW = 4 / sizeof(T);
     constexpr size_t TILE = size_t(THREADS) * V * UNROLL;
     constexpr uint32_t VMASK = V >= 32 ? 0xFFFFFFFFu : ((1u << (V & 31)) - 1u);
+    constexpr uint32_t BIAS = !SG ? 0u : (sizeof(T) == 1 ? 0x80808080u : (sizeof(T) == 2 ? 0x80008000u : 0x80000000u));
+    constexpr uint32_t LB = !SG ? 0u : (sizeof(T) == 1 ? 0x80u : (sizeof(T) == 2 ? 0x8000u : 0x80000000u));
     const size_t full = n / TILE;
     int64_t sum = 0;
-    uint64_t sq = 0, count = 0;
+    uint64_t sum_u = 0;                      // 32-bit cells: zero-extended (biased when signed) sum of the tiled part
+    uint64_t sq = 0, sq_hi = 0, count = 0;   // sq_hi: upper halves of the 32-bit cells' squares, weight 2^32
+    uint32_t pmin = 0xFFFFFFFFu, pmax = 0u;  // 8/16-bit: two 16-bit lanes; 32-bit: one biased value
 
     for (size_t t = blockIdx.x; t < full; t += gridDim.x) {
         const size_t base = t * TILE + size_t(threadIdx.x) * V;
@@ -172,22 +180,28 @@ __global__ void __launch_bounds__(THREADS) int_moments_kernel(const T* __restric
             w[u] = ld_stream<uint32_t, W>(reinterpret_cast<const uint32_t*>(a + c));
             if constexpr (MASKED) mw[u] = (__ldg(m + c / 32) >> (c % 32)) & VMASK;
         }
-        int32_t ts = 0;      // |sum| of one thread's tile share: 128 cells x 2^15
-        uint32_t tq8 = 0;    // 8-bit: 128 cells x 2^16
+        int32_t ts = 0;      // 8/16-bit: one thread's share of a tile, at most 128 cells x 2^15
+        uint32_t tq8 = 0;    // 8-bit squares: 128 cells x 2^16
         uint64_t tq16 = 0;   // 16-bit squares reach 2^32 each
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
             for (int j = 0; j < W; ++j) {
                 uint32_t x = w[u].v[j];
+                uint32_t kmin = x ^ BIAS, kmax = x ^ BIAS;
                 if constexpr (MASKED) {
                     const uint32_t b = (mw[u] >> (CPW * j)) & ((1u << CPW) - 1u);
                     uint32_t sel;
                     if constexpr (sizeof(T) == 1) sel = ((b * 0x00204081u) & 0x01010101u) * 0xFFu;  // 4 bits -> 4 byte masks
-                    else sel = ((b & 1u) * 0xFFFFu) | ((b >> 1) * 0xFFFF0000u);
-                    x &= sel;  // a masked-out cell becomes 0: contributes nothing to either sum
+                    else if constexpr (sizeof(T) == 2) sel = ((b * 0x00008001u) & 0x00010001u) * 0xFFFFu;  // 2 bits -> 2 lane masks
+                    else sel = 0u - b;
+                    x &= sel;
+                    kmin |= ~sel;
+                    kmax &= sel;
                 }
                 if constexpr (sizeof(T) == 1) {
+                    pmin = __vimin3_u16x2(pmin, __byte_perm(kmin, 0u, 0x4240), __byte_perm(kmin, 0u, 0x4341));
+                    pmax = __vimax3_u16x2(pmax, __byte_perm(kmax, 0u, 0x4240), __byte_perm(kmax, 0u, 0x4341));
                     if constexpr (SG) {
                         ts = __dp4a(static_cast<int>(x), 0x01010101, ts);
                         tq8 = static_cast<uint32_t>(__dp4a(static_cast<int>(x), static_cast<int>(x), static_cast<int>(tq8)));
@@ -195,7 +209,9 @@ __global__ void __launch_bounds__(THREADS) int_moments_kernel(const T* __restric
                         ts = static_cast<int32_t>(__dp4a(x, 0x01010101u, static_cast<uint32_t>(ts)));
                         tq8 = __dp4a(x, x, tq8);
                     }
-                } else {
+                } else if constexpr (sizeof(T) == 2) {
+                    pmin = __vminu2(pmin, kmin);
+                    pmax = __vmaxu2(pmax, kmax);
                     if constexpr (SG) {
                         const int lo = static_cast<int>(x << 16) >> 16, hi = static_cast<int>(x) >> 16;
                         ts += lo + hi;
@@ -205,13 +221,32 @@ __global__ void __launch_bounds__(THREADS) int_moments_kernel(const T* __restric
                         ts += static_cast<int32_t>(lo + hi);
                         tq16 += static_cast<uint64_t>(lo * lo) + static_cast<uint64_t>(hi * hi);
                     }
+                } else {
+                    pmin = min(pmin, kmin);
+                    pmax = max(pmax, kmax);
+                    // signed cells are summed biased (kmax = (x ^ 2^31) & sel, zero for a masked-out cell) and squared
+                    // through |x|: zero-extending adds and one unsigned 32x32->64 multiply per cell
+                    uint32_t mag = x;
+                    if constexpr (SG) { sum_u += kmax; mag = static_cast<uint32_t>(abs(static_cast<int>(x))); }
+                    else sum_u += x;
+                    const uint64_t q = static_cast<uint64_t>(mag) * mag;
+                    sq += q & 0xFFFFFFFFull;
+                    sq_hi += q >> 32;
                 }
             }
             if constexpr (MASKED) count += __popc(mw[u]);
         }
-        sum += ts;
-        sq += sizeof(T) == 1 ? static_cast<uint64_t>(tq8) : tq16;
+        if constexpr (sizeof(T) <= 2) {
+            sum += ts;
+            sq += sizeof(T) == 1 ? static_cast<uint64_t>(tq8) : tq16;
+        }
         if constexpr (!MASKED) count += uint64_t(V) * UNROLL;
+    }
+    uint32_t lo, hi;
+    if constexpr (sizeof(T) <= 2) { lo = min(pmin & 0xFFFFu, pmin >> 16); hi = max(pmax & 0xFFFFu, pmax >> 16); }
+    else {
+        lo = pmin; hi = pmax;
+        sum = static_cast<int64_t>(sum_u) - (SG ? static_cast<int64_t>(count << 31) : 0);  // take the bias off: 2^31 per valid cell
     }
     if (blockIdx.x == full % gridDim.x) {  // ragged tail, one cell per thread
         for (size_t i = full * TILE + threadIdx.x; i < n; i += THREADS) {
@@ -219,33 +254,57 @@ __global__ void __launch_bounds__(THREADS) int_moments_kernel(const T* __restric
             if constexpr (MASKED) valid = (m[i / 32] >> (i % 32)) & 1u;
             if (!valid) continue;
             const int64_t x = static_cast<int64_t>(a[i]);
+            const uint32_t k = static_cast<uint32_t>(static_cast<bits_t<T>>(a[i])) ^ LB;
+            lo = min(lo, k);
+            hi = max(hi, k);
             sum += x;
-            sq += static_cast<uint64_t>(x * x);
+            const uint64_t q = static_cast<uint64_t>(x * x);
+            sq += q & 0xFFFFFFFFull;
+            sq_hi += q >> 32;
             ++count;
         }
     }
-    // per-CTA totals fit 64 bits (a CTA sees fewer than 2^28 cells of at most 2^32 each); the cross-CTA sums are
-    // 128-bit through carry-tracking atomics, as in moments_kernel
+    // per-CTA totals fit 64 bits (a CTA sees fewer than 2^28 cells, see the launcher)
     sum = static_cast<int64_t>(warp_sum(static_cast<uint64_t>(sum)));
     sq = warp_sum(sq);
+    sq_hi = warp_sum(sq_hi);
     count = warp_sum(count);
-    __shared__ uint64_t sh[THREADS / 32][3];
+    lo = warp_min(lo);
+    hi = warp_max(hi);
+    __shared__ uint64_t sh[THREADS / 32][4];
+    __shared__ uint32_t shk[THREADS / 32][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) { sh[warp][0] = static_cast<uint64_t>(sum); sh[warp][1] = sq; sh[warp][2] = count; }
+    if (lane == 0) {
+        sh[warp][0] = static_cast<uint64_t>(sum); sh[warp][1] = sq; sh[warp][2] = sq_hi; sh[warp][3] = count;
+        shk[warp][0] = lo; shk[warp][1] = hi;
+    }
     __syncthreads();
-    if (threadIdx.x < 3) {
+    if (threadIdx.x < 4) {
         uint64_t t = sh[0][threadIdx.x];
 #pragma unroll
         for (int wv = 1; wv < THREADS / 32; ++wv) t += sh[wv][threadIdx.x];
-        if (threadIdx.x == 2) {
+        if (threadIdx.x == 3) {
             atomicAdd(acc, static_cast<unsigned long long>(t));
         } else {
-            unsigned long long* dst = acc + 1 + 2 * threadIdx.x;
-            const unsigned long long old = atomicAdd(dst, static_cast<unsigned long long>(t));
-            const unsigned long long carry = (old + t < old) ? 1ull : 0ull;
-            const unsigned long long ext = (threadIdx.x == 0 && static_cast<int64_t>(t) < 0) ? ~0ull : 0ull;  // sign of A
-            atomicAdd(dst + 1, ext + carry);
+            // 128-bit add of {A: sign-extended t | B: t | B: t * 2^32} with the carry taken from the low word's old value
+            unsigned long long add_lo = t, add_hi = 0;
+            if (threadIdx.x == 0) add_hi = static_cast<int64_t>(t) < 0 ? ~0ull : 0ull;
+            if (threadIdx.x == 2) { add_lo = t << 32; add_hi = t >> 32; }
+            unsigned long long* dst = acc + (threadIdx.x == 0 ? 1 : 3);
+            const unsigned long long old = atomicAdd(dst, add_lo);
+            const unsigned long long carry = (old + add_lo < old) ? 1ull : 0ull;
+            atomicAdd(dst + 1, add_hi + carry);
         }
+    } else if (threadIdx.x == 4) {
+        uint32_t k = shk[0][0];
+#pragma unroll
+        for (int wv = 1; wv < THREADS / 32; ++wv) k = min(k, shk[wv][0]);
+        atomicMin(acc + 5, static_cast<unsigned long long>(k));
+    } else if (threadIdx.x == 5) {
+        uint32_t k = shk[0][1];
+#pragma unroll
+        for (int wv = 1; wv < THREADS / 32; ++wv) k = max(k, shk[wv][1]);
+        atomicMax(acc + 6, static_cast<unsigned long long>(k));
     }
 }
 

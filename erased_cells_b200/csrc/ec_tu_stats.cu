@@ -1,4 +1,5 @@
-// Moments pass of the statistics extension (10 cell types x masked/unmasked); see ec_stats.cuh.
+// Statistics extension: FP64 window moments (64-bit integers, floats) and the one-pass integer kernel (integers of at
+// most 32 bits), masked and unmasked; see ec_stats.cuh.
 #include "ec_internal.hpp"
 #include "ec_stats.cuh"
 
@@ -34,19 +35,21 @@ static cudaError_t moments_t(const Launch& Lc, const void* a, const uint32_t* ma
 
 cudaError_t launch_moments(const Launch& Lc, int ct, const void* a, const uint32_t* mask, size_t n, double pivot, double scale,
                            unsigned long long* acc) {
-    switch (ct) {
-#define X(id, p) case id: return moments_t<p>(Lc, a, mask, n, pivot, scale, acc);
-        EC_WITH_CT(X)
-#undef X
+    switch (ct) {  // 64-bit integers and floats; narrower integers take the exact integer route (launch_int_stats)
+        case EC_UINT64: return moments_t<uint64_t>(Lc, a, mask, n, pivot, scale, acc);
+        case EC_INT64: return moments_t<int64_t>(Lc, a, mask, n, pivot, scale, acc);
+        case EC_FLOAT32: return moments_t<float>(Lc, a, mask, n, pivot, scale, acc);
+        case EC_FLOAT64: return moments_t<double>(Lc, a, mask, n, pivot, scale, acc);
     }
     return cudaErrorInvalidValue;
 }
 
-// 8/16-bit cells: integer moments, no FP64 (see ec_stats.cuh). A CTA must see fewer than 2^28 cells for its 64-bit
-// partials: the grid is never capped below n / 2^28 tiles' worth.
+// Integer cells of at most 32 bits: min, max, count, sum x, sum x^2 in one pass (see ec_stats.cuh). acc[7], with
+// acc[5] preset to all ones (min) and acc[6] to 0 (max); both hold biased (x ^ sign bit) cells. A CTA must see fewer
+// than 2^28 cells for its 64-bit partials: the grid is never capped below n / 2^28.
 constexpr int kIntStatUnroll = 4;
 template <class T>
-static cudaError_t int_moments_t(const Launch& Lc, const void* a, const uint32_t* mask, size_t n, unsigned long long* acc) {
+static cudaError_t int_stats_t(const Launch& Lc, const void* a, const uint32_t* mask, size_t n, unsigned long long* acc) {
     constexpr int V = EC_VB / sizeof(T);
     constexpr size_t TILE = size_t(kStatThreads) * V * kIntStatUnroll;
     size_t grid = n / TILE;
@@ -55,19 +58,21 @@ static cudaError_t int_moments_t(const Launch& Lc, const void* a, const uint32_t
     if (grid > cap) grid = cap;
     if (grid == 0) grid = 1;
     if (mask)
-        int_moments_kernel<T, true, EC_VB, kIntStatUnroll, kStatThreads><<<int(grid), kStatThreads, 0, Lc.stream>>>(
+        int_stats_kernel<T, true, EC_VB, kIntStatUnroll, kStatThreads><<<int(grid), kStatThreads, 0, Lc.stream>>>(
             static_cast<const T*>(a), mask, n, acc);
     else
-        int_moments_kernel<T, false, EC_VB, kIntStatUnroll, kStatThreads><<<int(grid), kStatThreads, 0, Lc.stream>>>(
+        int_stats_kernel<T, false, EC_VB, kIntStatUnroll, kStatThreads><<<int(grid), kStatThreads, 0, Lc.stream>>>(
             static_cast<const T*>(a), nullptr, n, acc);
     return cudaGetLastError();
 }
-cudaError_t launch_int_moments(const Launch& Lc, int ct, const void* a, const uint32_t* mask, size_t n, unsigned long long* acc) {
+cudaError_t launch_int_stats(const Launch& Lc, int ct, const void* a, const uint32_t* mask, size_t n, unsigned long long* acc) {
     switch (ct) {
-        case EC_UINT8: return int_moments_t<uint8_t>(Lc, a, mask, n, acc);
-        case EC_UINT16: return int_moments_t<uint16_t>(Lc, a, mask, n, acc);
-        case EC_INT8: return int_moments_t<int8_t>(Lc, a, mask, n, acc);
-        case EC_INT16: return int_moments_t<int16_t>(Lc, a, mask, n, acc);
+        case EC_UINT8: return int_stats_t<uint8_t>(Lc, a, mask, n, acc);
+        case EC_UINT16: return int_stats_t<uint16_t>(Lc, a, mask, n, acc);
+        case EC_UINT32: return int_stats_t<uint32_t>(Lc, a, mask, n, acc);
+        case EC_INT8: return int_stats_t<int8_t>(Lc, a, mask, n, acc);
+        case EC_INT16: return int_stats_t<int16_t>(Lc, a, mask, n, acc);
+        case EC_INT32: return int_stats_t<int32_t>(Lc, a, mask, n, acc);
     }
     return cudaErrorInvalidValue;
 }

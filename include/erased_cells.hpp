@@ -151,6 +151,14 @@ struct LazyScope {  // RAII: `{ LazyScope lazy; auto ndvi = (nir - red) / (nir +
 };
 
 // ---- CellBuffer — src/buffer.rs; BufferOps — src/lib.rs:104-163 -----------------------------------------------
+// count / min / max / mean / population stddev of the valid cells — an extension (ec_statistics): the reference has no
+// statistics beyond min_max and Mask::counts. Order-independent definition, see DESIGN.md §4.6.
+struct Statistics {
+    uint64_t count;
+    CellValue min, max;
+    double mean, stddev;
+};
+
 class Mask;
 class CellBuffer {
     ec_buf* h_ = nullptr;
@@ -193,6 +201,11 @@ public:
         CellValue a, b;
         detail::check(ec_buf_min_max(h_, nullptr, &a.v, &b.v));
         return {a, b};
+    }
+    Statistics statistics() const {  // extension: the reference stops at min_max
+        ec_statistics s;
+        detail::check(ec_buf_statistics(h_, nullptr, &s));
+        return Statistics{s.count, CellValue(s.min), CellValue(s.max), s.mean, s.stddev};
     }
     template <class T> std::vector<T> to_vec() const {  // src/buffer.rs:175-185
         const CellBuffer r = convert(CellEncoding<T>::cell_type());
@@ -358,6 +371,11 @@ public:
         CellValue a, b;
         detail::check(ec_buf_min_max(buf_.h_, mask_.h_, &a.v, &b.v));
         return {a, b};
+    }
+    Statistics statistics() const {  // of the valid cells (extension)
+        ec_statistics s;
+        detail::check(ec_buf_statistics(buf_.h_, mask_.h_, &s));
+        return Statistics{s.count, CellValue(s.min), CellValue(s.max), s.mean, s.stddev};
     }
     template <class T> std::vector<T> to_vec() const { return buf_.to_vec<T>(); }
     template <class T> std::vector<T> to_vec_with_nodata(NoData<T> no_data) const {  // :137-152

@@ -415,9 +415,12 @@ def tight_min_max(a, mask=None):
 # of summation order, grid size and the number of GPUs:
 #   1. (mn, mx) = min_max of the valid cells; x = to_f64(cell)
 #   2. pivot p = fl(xmin/2 + xmax/2); E = binary exponent with max|x - p| < 2^E (clamped to [-1000, 1024])
-#   3. per valid cell: y = fl(fl(x - p) * 2^-E), z = fl(y * y); each is split into two 48-bit fixed-point
-#      windows (units 2^-47 and 2^-95, round-to-nearest-even at the second), summed EXACTLY as integers
-#   4. S1, S2 -> m1 = S1/n, m2 = S2/n, var = max(m2 - m1*m1, 0); mean = p + m1*2^E; stddev = sqrt(var)*2^E
+#   3a. integer cells of at most 32 bits: y = (x - p) * 2^-E is exact; S1 = RN(sum y), S2 = RN(sum y^2), the sums
+#       taken exactly (they follow from count, A = sum x, B = sum x^2 and s = 2p = min + max)
+#   3b. 64-bit integers and floats: y = fl(fl(x - p) * 2^-E), z = fl(y * y); each is split into two 48-bit
+#       fixed-point windows (units 2^-47 and 2^-95, round-to-nearest-even at the second), the four integer
+#       streams are summed EXACTLY; S1 = fl(fl(X1) * 2^-47 + fl(X2) * 2^-95), S2 likewise from the z windows
+#   4. m1 = S1/n, m2 = S2/n, var = max(m2 - m1*m1, 0); mean = p + m1*2^E; stddev = sqrt(var)*2^E
 # numpy float64 arithmetic below is IEEE binary64 with one rounding per operation, like the device code
 # (__dadd_rn/__dmul_rn) and the host finish.
 _C1 = 48.0                      # 1.5 * 2^5: ulp = 2^-47
@@ -459,11 +462,18 @@ def _isum(x: np.ndarray) -> int:
     return sum(int(x[i:i + (1 << 14)].sum(dtype=np.int64)) for i in range(0, len(x), 1 << 14))
 
 
+def integer_route(ct: int) -> bool:
+    return is_integral(ct) and size_of(ct) <= 4
+
+
 def moments_raw(a, mask, pivot: float, exp2: int):
-    """[count, sum X1, sum X2, sum Z1, sum Z2] as python ints."""
+    """[count, sum X1, sum X2, sum Z1, sum Z2] — or, on the integer route, [count, sum x, sum x^2, 0, 0] — as python ints."""
     a = _c(a)
     if mask is not None:
         a = a[np.ascontiguousarray(mask, dtype=bool)]
+    if integer_route(ct_of(a)):
+        xs = [int(v) for v in a]
+        return [len(xs), sum(xs), sum(v * v for v in xs), 0, 0]
     with np.errstate(all="ignore"):
         y = (a.astype(np.float64) - np.float64(pivot)) * np.float64(np.ldexp(1.0, -exp2))
         x1, x2 = _windows(y)
@@ -485,8 +495,13 @@ def statistics_finish(raws, mn: Value, mx: Value):
             out["mean"] = lo if lo == -math.inf else hi
         return out
     n = float(tot[0])
-    s1 = math.ldexp(float(tot[1]), -47) + math.ldexp(float(tot[2]), -95)
-    s2 = math.ldexp(float(tot[3]), -47) + math.ldexp(float(tot[4]), -95)
+    if integer_route(mn.ct):
+        cnt, A, B, s2p = tot[0], tot[1], tot[2], int(p * 2.0)  # y = (2x - s) / 2 exactly
+        s1 = math.ldexp(float(2 * A - cnt * s2p), -1 - e)   # python int -> float is round-to-nearest-even
+        s2 = math.ldexp(float(4 * B - 4 * s2p * A + cnt * s2p * s2p), -2 - 2 * e)
+    else:
+        s1 = math.ldexp(float(tot[1]), -47) + math.ldexp(float(tot[2]), -95)
+        s2 = math.ldexp(float(tot[3]), -47) + math.ldexp(float(tot[4]), -95)
     m1, m2 = s1 / n, s2 / n
     var = m2 - m1 * m1
     if var < 0:

@@ -372,6 +372,22 @@ impl MaskedCellBuffer {
         check(unsafe { ec_buf_min_max((self.0).0, (self.1).0, &mut a, &mut b) }).unwrap();
         (from_ffi(a), from_ffi(b))
     }
+    /// Extension (not in the crate): count / min / max / mean / population stddev of the valid cells.
+    pub fn statistics(&self) -> Statistics {
+        let z = ec_value { ct: 0, pad: [0; 7], bits: 0 };
+        let mut s = ec_statistics { count: 0, min: z, max: z, mean: 0.0, stddev: 0.0 };
+        check(unsafe { ec_buf_statistics((self.0).0, (self.1).0, &mut s) }).unwrap();
+        Statistics { count: s.count, min: from_ffi(s.min), max: from_ffi(s.max), mean: s.mean, stddev: s.stddev }
+    }
+}
+/// Result of the `statistics()` extension.
+#[derive(Debug, Clone, Copy, PartialEq)]
+pub struct Statistics {
+    pub count: u64,
+    pub min: CellValue,
+    pub max: CellValue,
+    pub mean: f64,
+    pub stddev: f64,
 }
 macro_rules! mcb_bin_op {
     // src/masked/masked_buffer.rs:323-370: data on all cells, mask = lmask & rmask, one fused launch

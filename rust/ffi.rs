@@ -14,6 +14,16 @@ pub struct ec_value {
     pub pad: [u8; 7],
     pub bits: u64,
 }
+/// extension: statistics of the valid cells (the crate itself stops at min_max / counts)
+#[repr(C)]
+#[derive(Copy, Clone)]
+pub struct ec_statistics {
+    pub count: u64,
+    pub min: ec_value,
+    pub max: ec_value,
+    pub mean: f64,
+    pub stddev: f64,
+}
 #[repr(C)] pub struct ec_buf { _p: [u8; 0] }
 #[repr(C)] pub struct ec_mask { _p: [u8; 0] }
 #[repr(C)] pub struct ec_comm { _p: [u8; 0] }
@@ -49,6 +59,7 @@ extern "C" {
     pub fn ec_buf_neg(b: *const ec_buf, out: *mut *mut ec_buf) -> ec_status;
     pub fn ec_buf_convert(b: *const ec_buf, ct: u8, out: *mut *mut ec_buf) -> ec_status;
     pub fn ec_buf_min_max(b: *const ec_buf, mask: *const ec_mask, mn: *mut ec_value, mx: *mut ec_value) -> ec_status;
+    pub fn ec_buf_statistics(b: *const ec_buf, mask: *const ec_mask, out: *mut ec_statistics) -> ec_status;
     pub fn ec_buf_cmp(l: *const ec_buf, r: *const ec_buf, ordering: *mut c_int) -> ec_status;
     // Mask
     pub fn ec_mask_from_bools(bools: *const u8, len: usize, out: *mut *mut ec_mask) -> ec_status;

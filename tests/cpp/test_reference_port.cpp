@@ -251,9 +251,28 @@ static void lazy_tests() {
     CHECK(ec_get_lazy() == 0);
 }
 
+// The statistics extension has no reference test to port: small cases whose exact answers are representable.
+static void statistics_tests() {
+    const Statistics s = CellBuffer::from_vec(std::vector<uint8_t>{2, 4, 4, 4, 5, 5, 7, 9}).statistics();
+    CHECK(s.count == 8 && s.min == CellValue(uint8_t(2)) && s.max == CellValue(uint8_t(9)) && s.mean == 5.0 && s.stddev == 2.0);
+    const Statistics f = CellBuffer::from_vec(std::vector<float>{1.5f, -0.5f, 2.5f, 0.5f}).statistics();
+    CHECK(f.count == 4 && f.mean == 1.0 && f.stddev == std::sqrt(1.25));
+    MaskedCellBuffer m = MaskedCellBuffer::from_vec_with_nodata(std::vector<int16_t>{-32768, 10, 20, -32768, 30}, NoData<int16_t>());
+    const Statistics ms = m.statistics();
+    CHECK(ms.count == 3 && ms.min == CellValue(int16_t(10)) && ms.max == CellValue(int16_t(30)) && ms.mean == 20.0);
+    CHECK(ms.stddev == std::sqrt(200.0 / 3.0));
+    const Statistics e = CellBuffer::with_defaults(0, CellType::Float64).statistics();
+    CHECK(e.count == 0 && std::isnan(e.mean) && std::isnan(e.stddev));
+    const Statistics inf = CellBuffer::from_vec(std::vector<double>{1.0, HUGE_VAL}).statistics();
+    CHECK(inf.count == 2 && inf.mean == HUGE_VAL && std::isnan(inf.stddev));
+    const Statistics big = CellBuffer::from_vec(std::vector<uint32_t>{4000000000u, 4000000002u}).statistics();
+    CHECK(big.mean == 4000000001.0 && big.stddev == 1.0);
+}
+
 int main() {
     try {
         can_union(); ctype_misc(); value_tests(); buffer_tests(); mask_tests(); nodata_tests(); masked_tests(); lazy_tests();
+        statistics_tests();
     } catch (const std::exception& e) {
         std::fprintf(stderr, "exception: %s\n", e.what());
         return 2;

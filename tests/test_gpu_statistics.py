@@ -95,7 +95,7 @@ def test_strip_and_grid_independence_at_scale(orc):
     """2^26 + ragged cells made on the device; the whole-buffer result must equal the finish over three unequal strips'
     raw sums (different grids, different tails) and the oracle on the downloaded cells."""
     n = (1 << 26) + 12345
-    for ct, lo, hi in ((CellType.UInt16, 5000, 40000), (CellType.Float32, -1.0e4, 1.0e4)):
+    for ct, lo, hi in ((CellType.UInt16, 5000, 40000), (CellType.Int32, -2.0e9, 2.0e9), (CellType.Float32, -1.0e4, 1.0e4)):
         buf = synth.device(ct, n, 0xEC77, kind=synth.REAL_RANGE, lo=lo, hi=hi)
         whole = buf.statistics()
         kind, p, e = sharding.statistics_plan(whole.min, whole.max)
