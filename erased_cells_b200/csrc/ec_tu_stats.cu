@@ -13,23 +13,32 @@ namespace ec {
 // register budget goes to the eight accumulators.
 constexpr int kStatThreads = 256;
 constexpr int kStatUnroll = 2;
-constexpr int kStatCtasPerSm = 8;
+
+// Persistent grids are sized to what is actually resident (register use differs between the instantiations: a grid of
+// 8 CTAs per SM over a kernel that fits 6 runs a second, one-third-full wave).
+template <class K> static size_t resident_ctas(K kernel, const Launch& Lc) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kStatThreads, 0) != cudaSuccess || per_sm < 1) {
+        (void)cudaGetLastError();
+        per_sm = 1;
+    }
+    return size_t(Lc.sm_count) * per_sm;
+}
 
 template <class T>
 static cudaError_t moments_t(const Launch& Lc, const void* a, const uint32_t* mask, size_t n, double pivot, double scale,
                              unsigned long long* acc) {
     constexpr int V = EC_VB / sizeof(T);
     constexpr size_t TILE = size_t(kStatThreads) * V * kStatUnroll;
+    auto masked = moments_kernel<T, true, EC_VB, kStatUnroll, kStatThreads>;
+    auto plain = moments_kernel<T, false, EC_VB, kStatUnroll, kStatThreads>;
+    static const size_t cap_masked = resident_ctas(masked, Lc), cap_plain = resident_ctas(plain, Lc);
     size_t grid = n / TILE;
-    const size_t cap = size_t(Lc.sm_count) * kStatCtasPerSm;
+    const size_t cap = mask ? cap_masked : cap_plain;
     if (grid > cap) grid = cap;
     if (grid == 0) grid = 1;
-    if (mask)
-        moments_kernel<T, true, EC_VB, kStatUnroll, kStatThreads><<<int(grid), kStatThreads, 0, Lc.stream>>>(
-            static_cast<const T*>(a), mask, n, pivot, scale, acc);
-    else
-        moments_kernel<T, false, EC_VB, kStatUnroll, kStatThreads><<<int(grid), kStatThreads, 0, Lc.stream>>>(
-            static_cast<const T*>(a), nullptr, n, pivot, scale, acc);
+    if (mask) masked<<<int(grid), kStatThreads, 0, Lc.stream>>>(static_cast<const T*>(a), mask, n, pivot, scale, acc);
+    else plain<<<int(grid), kStatThreads, 0, Lc.stream>>>(static_cast<const T*>(a), nullptr, n, pivot, scale, acc);
     return cudaGetLastError();
 }
 
@@ -52,17 +61,16 @@ template <class T>
 static cudaError_t int_stats_t(const Launch& Lc, const void* a, const uint32_t* mask, size_t n, unsigned long long* acc) {
     constexpr int V = EC_VB / sizeof(T);
     constexpr size_t TILE = size_t(kStatThreads) * V * kIntStatUnroll;
+    auto masked = int_stats_kernel<T, true, EC_VB, kIntStatUnroll, kStatThreads>;
+    auto plain = int_stats_kernel<T, false, EC_VB, kIntStatUnroll, kStatThreads>;
+    static const size_t cap_masked = resident_ctas(masked, Lc), cap_plain = resident_ctas(plain, Lc);
     size_t grid = n / TILE;
-    size_t cap = size_t(Lc.sm_count) * kStatCtasPerSm;
+    size_t cap = mask ? cap_masked : cap_plain;
     if (cap < (n >> 28) + 1) cap = (n >> 28) + 1;
     if (grid > cap) grid = cap;
     if (grid == 0) grid = 1;
-    if (mask)
-        int_stats_kernel<T, true, EC_VB, kIntStatUnroll, kStatThreads><<<int(grid), kStatThreads, 0, Lc.stream>>>(
-            static_cast<const T*>(a), mask, n, acc);
-    else
-        int_stats_kernel<T, false, EC_VB, kIntStatUnroll, kStatThreads><<<int(grid), kStatThreads, 0, Lc.stream>>>(
-            static_cast<const T*>(a), nullptr, n, acc);
+    if (mask) masked<<<int(grid), kStatThreads, 0, Lc.stream>>>(static_cast<const T*>(a), mask, n, acc);
+    else plain<<<int(grid), kStatThreads, 0, Lc.stream>>>(static_cast<const T*>(a), nullptr, n, acc);
     return cudaGetLastError();
 }
 cudaError_t launch_int_stats(const Launch& Lc, int ct, const void* a, const uint32_t* mask, size_t n, unsigned long long* acc) {

@@ -33,7 +33,7 @@ if rank == 0:
     print("peer exchange over NVLink (fused one-kernel sharded reductions):", comm_obj.peer_exchange)
 
 ok = True
-for ct in (CellType.Float32, CellType.Int16, CellType.UInt8, CellType.Float64, CellType.UInt64):
+for ct in (CellType.Float32, CellType.Int16, CellType.UInt8, CellType.Float64, CellType.UInt64, CellType.Int32):
     kw = dict(kind=synth.FULL_BITS) if ct != CellType.Float32 else dict(kind=synth.REAL_RANGE, lo=-1e4, hi=1e4)
     strip = synth.device(ct, ln, 0xEC40 + int(ct), index_offset=off, **kw)
     # reference: the same raster reduced on ONE GPU (every rank builds the whole raster for the check)
@@ -51,9 +51,18 @@ for ct in (CellType.Float32, CellType.Int16, CellType.UInt8, CellType.Float64, C
     d, n = C.c_size_t(), C.c_size_t()
     ec._lib.check(L.ec_mask_counts_sharded(comm, ms.mask()._h, C.byref(d), C.byref(n)))
     good &= (b[0].bits, b[1].bits) == (wm[0].bits, wm[1].bits) and (d.value, n.value) == mw.counts() == sharding.counts_sharded(ms.mask())
+    # statistics (extension): global min/max -> one plan -> per-strip exact sums -> all-gather -> finish; must equal
+    # the single-GPU result bit for bit, through both min/max plumbings, masked and unmasked
+    def same_stats(x, y):
+        return (x.count, x.min.bits, x.max.bits) == (y.count, y.min.bits, y.max.bits) and \
+            np.array_equal(np.array([x.mean, x.stddev]).view(np.uint64), np.array([y.mean, y.stddev]).view(np.uint64))
+    good_stats = same_stats(sharding.statistics_sharded(strip), whole.statistics())
+    good_stats &= same_stats(sharding.statistics_sharded(strip, None, None, comm_obj), whole.statistics())
+    good_stats &= same_stats(sharding.statistics_sharded(strip, ms.mask(), None, comm_obj), mw.statistics())
     if rank == 0:
-        print(f"{ct}: sharded x{world} == single GPU: {good}  min/max bits {a[0].bits:#x} {a[1].bits:#x} counts {(d.value, n.value)}")
-    ok &= good
+        print(f"{ct}: sharded x{world} == single GPU: {good}  min/max bits {a[0].bits:#x} {a[1].bits:#x} counts {(d.value, n.value)}; "
+              f"statistics {good_stats} {whole.statistics()}")
+    ok &= good and good_stats
     del whole, strip, ms, mw
 
 # the sharded raster types: NDVI on the Landsat-like fixture layout, every rank uploads only its strip
