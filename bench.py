@@ -522,9 +522,9 @@ def other_configs(ec, L, torch, dist, rank, world, barrier, max_over_ranks, peak
         res["c4_f32_32768_min_max_sharded_fused"] = entry(timed(lambda: comm.min_max(strip), 10), 4.0 * n4, n4, scaling="strong", shards=world,
                                                           peer_exchange=comm.peer_exchange, result_bits=[hex(got[0].bits), hex(got[1].bits)],
                                                           note="ec_buf_min_max_sharded: one kernel per GPU when peer_exchange is true, else kernel + NCCL")
-        st = sharding.statistics_sharded(strip, None, None, comm)
-        res["c4_f32_32768_statistics_sharded"] = entry(timed(lambda: sharding.statistics_sharded(strip, None, None, comm), 5), 4.0 * n4, n4, scaling="strong", shards=world,
-                                                       result=[st.count, st.mean, st.stddev], note="extension: fused sharded min_max, FP64 moments pass per strip, all-gather of 72 B, host finish")
+        st = comm.statistics(strip)
+        res["c4_f32_32768_statistics_sharded"] = entry(timed(lambda: comm.statistics(strip), 5), 4.0 * n4, n4, scaling="strong", shards=world,
+                                                       result=[st.count, st.mean, st.stddev], note="extension, ec_buf_statistics_sharded: fused sharded min_max, FP64 moments pass per strip, one all-reduce of 136 B, host finish")
         comm.close()
     else:
         st = strip.statistics()

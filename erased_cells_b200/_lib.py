@@ -178,6 +178,7 @@ def _signatures():
         "ec_comm_allreduce_sum_u64": (S, [VP, VP, SZ]),
         "ec_buf_min_max_sharded": (S, [VP, VP, VP, PV, PV]),
         "ec_mask_counts_sharded": (S, [VP, VP, PSZ, PSZ]),
+        "ec_buf_statistics_sharded": (S, [VP, VP, VP, C.POINTER(Statistics)]),
         "ec_buf_synth": (S, [U8, SZ, U64, U64, I, C.c_double, C.c_double, U64, PV, PVP]),
     }
 

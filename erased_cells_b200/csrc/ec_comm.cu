@@ -15,7 +15,7 @@
 struct ec_comm {
     ncclComm_t comm;
     int n_ranks, rank;
-    int64_t* dkeys;   // 4 device words for in-place all-reduce
+    int64_t* dkeys;   // 4 device words for in-place all-reduce (+ 20 for the statistics limbs)
     int64_t* pinned;  // host mirror
     // NVLink peer exchange (see PeerExchange in ec_reduce.cuh): every rank's mailbox mapped into every rank
     bool peer_ok;
@@ -147,8 +147,8 @@ ec_status ec_comm_init_rank(const void* id128, int n_ranks, int rank, ec_comm** 
     c->n_ranks = n_ranks;
     c->rank = rank;
     if (ncclResult_t r = g_nccl.CommInitRank(&c->comm, n_ranks, id, rank)) { delete c; return nccl_fail(r, "ncclCommInitRank"); }
-    if (cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->dkeys), 4 * sizeof(int64_t))) { delete c; return cuda_fail(e, "cudaMalloc"); }
-    if (cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&c->pinned), 4 * sizeof(int64_t))) { delete c; return cuda_fail(e, "cudaMallocHost"); }
+    if (cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->dkeys), 24 * sizeof(int64_t))) { delete c; return cuda_fail(e, "cudaMalloc"); }
+    if (cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&c->pinned), 24 * sizeof(int64_t))) { delete c; return cuda_fail(e, "cudaMallocHost"); }
     if (ec_status s = peer_setup(c)) { ec_comm_destroy(c); return s; }
     *out = c;
     return EC_OK;
@@ -213,6 +213,44 @@ ec_status ec_mask_counts_sharded(ec_comm* c, const ec_mask* shard, size_t* data,
     *data = static_cast<size_t>(c->pinned[2]);
     *nodata = static_cast<size_t>(c->pinned[3]);
     return EC_OK;
+}
+// Statistics of a row-strip sharded raster (extension): global min/max (above) -> the same plan on
+// every rank -> this strip's exact moment sums -> one all-reduce(SUM) -> the same finish everywhere. The 128-bit
+// sums travel as 32-bit limbs in 64-bit words, so adding up to 64 ranks cannot lose a carry.
+ec_status ec_buf_statistics_sharded(ec_comm* c, const ec_buf* shard, const ec_mask* mask_or_null, ec_statistics* out) {
+    ec_value mn, mx;
+    if (ec_status s = ec_buf_min_max_sharded(c, shard, mask_or_null, &mn, &mx)) return s;
+    int kind, e;
+    double p;
+    if (ec_status s = ec_statistics_plan(&mn, &mx, &kind, &p, &e)) return s;
+    uint64_t raw[EC_MOMENT_WORDS] = {0};
+    if (kind == EC_STATS_REGULAR) {
+        if (ec_status s = ec_buf_moments(shard, mask_or_null, p, e, raw)) return s;
+    } else if (mask_or_null) {
+        size_t d = 0, nd = 0;
+        if (ec_status s = ec_mask_counts(mask_or_null, &d, &nd)) return s;
+        raw[0] = d;
+    } else {
+        raw[0] = ec_buf_len(shard);
+    }
+    uint64_t* limbs = reinterpret_cast<uint64_t*>(c->pinned + 4);
+    uint64_t* dlimbs = reinterpret_cast<uint64_t*>(c->dkeys + 4);
+    limbs[0] = raw[0];
+    for (int k = 0; k < 8; ++k) { limbs[1 + 2 * k] = raw[1 + k] & 0xFFFFFFFFull; limbs[2 + 2 * k] = raw[1 + k] >> 32; }
+    cudaStream_t st = static_cast<cudaStream_t>(ec_get_stream());
+    if (cudaError_t err = cudaMemcpyAsync(dlimbs, limbs, 17 * sizeof(uint64_t), cudaMemcpyHostToDevice, st)) return cuda_fail(err, "cudaMemcpyAsync(H2D)");
+    if (ec_status s = ec_comm_allreduce_sum_u64(c, dlimbs, 17)) return s;
+    if (cudaError_t err = cudaMemcpyAsync(limbs, dlimbs, 17 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st)) return cuda_fail(err, "cudaMemcpyAsync(D2H)");
+    if (cudaError_t err = cudaStreamSynchronize(st)) return cuda_fail(err, "cudaStreamSynchronize");
+    uint64_t total[EC_MOMENT_WORDS];
+    total[0] = limbs[0];
+    for (int a = 0; a < 4; ++a) {  // four 128-bit accumulators, each from four summed limbs, modulo 2^128
+        unsigned __int128 v = 0;
+        for (int j = 3; j >= 0; --j) v = (v << 32) + limbs[1 + 4 * a + j];
+        total[1 + 2 * a] = static_cast<uint64_t>(v);
+        total[2 + 2 * a] = static_cast<uint64_t>(v >> 64);
+    }
+    return ec_statistics_finish(total, 1, &mn, &mx, out);
 }
 
 }  // extern "C"

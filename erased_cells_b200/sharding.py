@@ -158,6 +158,12 @@ class Comm:
         check(lib().ec_mask_counts_sharded(self._h, mask._h, C.byref(d), C.byref(n)))
         return d.value, n.value
 
+    def statistics(self, shard: CellBuffer, mask: Mask | None = None) -> Statistics:
+        """statistics of the whole raster (extension): fused min/max, this strip's exact sums, one all-reduce, host finish"""
+        out = _lib.Statistics()
+        check(lib().ec_buf_statistics_sharded(self._h, shard._h, mask._h if mask is not None else None, C.byref(out)))
+        return Statistics(out)
+
     def close(self):
         if self._h:
             lib().ec_comm_destroy(self._h)
@@ -205,8 +211,8 @@ class ShardedCellBuffer:
     def min_max(self):
         return self.comm.min_max(self.strip)
 
-    def statistics(self, group=None) -> Statistics:
-        return statistics_sharded(self.strip, None, group, self.comm)
+    def statistics(self) -> Statistics:
+        return self.comm.statistics(self.strip)
 
     def gather(self) -> np.ndarray:
         """The whole raster on every rank's host (tests / small rasters)."""
@@ -245,5 +251,5 @@ class ShardedMaskedCellBuffer:
     def counts(self):
         return self.comm.counts(self.strip.mask())
 
-    def statistics(self, group=None) -> Statistics:
-        return statistics_sharded(self.strip.buffer(), self.strip.mask(), group, self.comm)
+    def statistics(self) -> Statistics:
+        return self.comm.statistics(self.strip.buffer(), self.strip.mask())

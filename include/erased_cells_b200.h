@@ -282,6 +282,8 @@ ec_status ec_comm_allreduce_sum_u64(ec_comm* c, uint64_t* device_buf, size_t cou
 ec_status ec_buf_min_max_sharded(ec_comm* c, const ec_buf* shard, const ec_mask* mask_or_null,
                                  ec_value* min_out, ec_value* max_out);
 ec_status ec_mask_counts_sharded(ec_comm* c, const ec_mask* shard, size_t* data, size_t* nodata);
+/* statistics of the whole raster from this rank's strip (extension; every rank calls it and gets the same result) */
+ec_status ec_buf_statistics_sharded(ec_comm* c, const ec_buf* shard, const ec_mask* mask_or_null, ec_statistics* out);
 
 /* ---- synthetic rasters (bench/test utility): counter-based splitmix64(seed ^ index) ----------- */
 /* cell i = f(h), h = splitmix64(seed ^ (index_offset + i)). kind 0: the low bits of h (uniform over

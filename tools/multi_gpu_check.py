@@ -59,6 +59,8 @@ for ct in (CellType.Float32, CellType.Int16, CellType.UInt8, CellType.Float64, C
     good_stats = same_stats(sharding.statistics_sharded(strip), whole.statistics())
     good_stats &= same_stats(sharding.statistics_sharded(strip, None, None, comm_obj), whole.statistics())
     good_stats &= same_stats(sharding.statistics_sharded(strip, ms.mask(), None, comm_obj), mw.statistics())
+    good_stats &= same_stats(comm_obj.statistics(strip), whole.statistics())               # all in the C ABI: ec_buf_statistics_sharded
+    good_stats &= same_stats(comm_obj.statistics(strip, ms.mask()), mw.statistics())
     if rank == 0:
         print(f"{ct}: sharded x{world} == single GPU: {good}  min/max bits {a[0].bits:#x} {a[1].bits:#x} counts {(d.value, n.value)}; "
               f"statistics {good_stats} {whole.statistics()}")
@@ -84,6 +86,7 @@ m_one = (MaskedCellBuffer.from_vec_with_nodata(nir_h.reshape(-1), nd) - MaskedCe
 m_one = m_one / (MaskedCellBuffer.from_vec_with_nodata(nir_h.reshape(-1), nd) + MaskedCellBuffer.from_vec_with_nodata(red_h.reshape(-1), nd))
 sharded_counts = m_ndvi.counts()  # collectives: every rank calls them
 good &= sharded_counts == m_one.counts() and tuple(v.bits for v in m_ndvi.min_max()) == tuple(v.bits for v in m_one.min_max())
+good &= same_stats(m_ndvi.statistics(), m_one.statistics()) and same_stats(ndvi.statistics(), one.statistics())
 if rank == 0:
     print(f"ShardedCellBuffer / ShardedMaskedCellBuffer NDVI (1031 x 512, ragged strips) == single GPU: {good}, counts {sharded_counts}")
 ok &= good
