@@ -54,6 +54,12 @@ __device__ __forceinline__ void moment_windows(double v, uint64_t& w1, uint64_t&
     w1 += static_cast<uint64_t>(__double_as_longlong(t1));
     w2 += static_cast<uint64_t>(__double_as_longlong(t2));
 }
+// to_f64 for finite cells: the moments pass only runs when no valid cell is NaN or infinite, and a masked-out cell's
+// value is discarded, so the payload-preserving f32 widening of as_f64 is not needed here
+template <class T> __device__ __forceinline__ double finite_f64(T v) {
+    if constexpr (std::is_same<T, float>::value) return static_cast<double>(v);
+    else return as_f64(v);
+}
 constexpr uint64_t kMomentK1 = 0x4048000000000000ull;  // bits(48.0)
 constexpr uint64_t kMomentK2 = 0x3D48000000000000ull;  // bits(48.0 * 2^-48)
 
@@ -82,7 +88,7 @@ __global__ void __launch_bounds__(THREADS) moments_kernel(const T* __restrict__ 
         for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
             for (int j = 0; j < V; ++j) {
-                double y = __dmul_rn(__dsub_rn(as_f64(va[u].v[j]), pivot), scale);
+                double y = __dmul_rn(__dsub_rn(finite_f64(va[u].v[j]), pivot), scale);
                 if constexpr (MASKED) y = ((w[u] >> j) & 1u) ? y : 0.0;  // a masked-out cell contributes 0 to every window
                 moment_windows(y, ts[0], ts[1]);
                 moment_windows(__dmul_rn(y, y), ts[2], ts[3]);
@@ -102,7 +108,7 @@ __global__ void __launch_bounds__(THREADS) moments_kernel(const T* __restrict__ 
             bool valid = true;
             if constexpr (MASKED) valid = (m[i / 32] >> (i % 32)) & 1u;
             if (!valid) continue;
-            const double y = __dmul_rn(__dsub_rn(as_f64(a[i]), pivot), scale);
+            const double y = __dmul_rn(__dsub_rn(finite_f64(a[i]), pivot), scale);
             uint64_t ts[4] = {0, 0, 0, 0};
             moment_windows(y, ts[0], ts[1]);
             moment_windows(__dmul_rn(y, y), ts[2], ts[3]);
@@ -190,10 +196,15 @@ __global__ void __launch_bounds__(THREADS) int_stats_kernel(const T* __restrict_
                 uint32_t x = w[u].v[j];
                 uint32_t kmin = x ^ BIAS, kmax = x ^ BIAS;
                 if constexpr (MASKED) {
-                    const uint32_t b = (mw[u] >> (CPW * j)) & ((1u << CPW) - 1u);
+                    [[maybe_unused]] const uint32_t b = (mw[u] >> (CPW * j)) & ((1u << CPW) - 1u);
                     uint32_t sel;
                     if constexpr (sizeof(T) == 1) sel = ((b * 0x00204081u) & 0x01010101u) * 0xFFu;  // 4 bits -> 4 byte masks
-                    else if constexpr (sizeof(T) == 2) sel = ((b * 0x00008001u) & 0x00010001u) * 0xFFFFu;  // 2 bits -> 2 lane masks
+                    else if constexpr (sizeof(T) == 2) {
+                        // 2 bits -> 2 lane masks: one multiply parks the two bits in the sign positions of bytes 2 and 3,
+                        // prmt's sign-replicate mode fans them out (the ALU pipe is what limits this kernel)
+                        const uint32_t v = (mw[u] & (3u << (2 * j))) * ((1u << (23 - 2 * j)) | (1u << (30 - 2 * j)));
+                        asm("prmt.b32 %0, %1, %1, 0xBBAA;" : "=r"(sel) : "r"(v));
+                    }
                     else sel = 0u - b;
                     x &= sel;
                     kmin |= ~sel;
@@ -212,15 +223,12 @@ __global__ void __launch_bounds__(THREADS) int_stats_kernel(const T* __restrict_
                 } else if constexpr (sizeof(T) == 2) {
                     pmin = __vminu2(pmin, kmin);
                     pmax = __vmaxu2(pmax, kmax);
-                    if constexpr (SG) {
-                        const int lo = static_cast<int>(x << 16) >> 16, hi = static_cast<int>(x) >> 16;
-                        ts += lo + hi;
-                        tq16 += static_cast<uint64_t>(static_cast<uint32_t>(lo * lo)) + static_cast<uint32_t>(hi * hi);
-                    } else {
-                        const uint32_t lo = x & 0xFFFFu, hi = x >> 16;
-                        ts += static_cast<int32_t>(lo + hi);
-                        tq16 += static_cast<uint64_t>(lo * lo) + static_cast<uint64_t>(hi * hi);
-                    }
+                    // sums run over the biased unsigned lanes u = x ^ 0x8000 (kmax; 0 for a masked-out lane) — no sign
+                    // extension; signed cells are put right after the loop: x = u - 2^15
+                    const uint32_t lo = kmax & 0xFFFFu, hi = kmax >> 16;
+                    ts = static_cast<int32_t>(__dp2a_lo(kmax, 0x00000101u, static_cast<uint32_t>(ts)));
+                    tq16 = static_cast<uint64_t>(lo) * lo + tq16;
+                    tq16 = static_cast<uint64_t>(hi) * hi + tq16;
                 } else {
                     pmin = min(pmin, kmin);
                     pmax = max(pmax, kmax);
@@ -243,8 +251,13 @@ __global__ void __launch_bounds__(THREADS) int_stats_kernel(const T* __restrict_
         if constexpr (!MASKED) count += uint64_t(V) * UNROLL;
     }
     uint32_t lo, hi;
-    if constexpr (sizeof(T) <= 2) { lo = min(pmin & 0xFFFFu, pmin >> 16); hi = max(pmax & 0xFFFFu, pmax >> 16); }
-    else {
+    if constexpr (sizeof(T) <= 2) {
+        lo = min(pmin & 0xFFFFu, pmin >> 16); hi = max(pmax & 0xFFFFu, pmax >> 16);
+        if constexpr (SG && sizeof(T) == 2) {  // sums were taken over u = x + 2^15: x = u - 2^15, x^2 = u^2 - 2^16 u + 2^30
+            sq = sq - (static_cast<uint64_t>(sum) << 16) + (count << 30);
+            sum -= static_cast<int64_t>(count << 15);
+        }
+    } else {
         lo = pmin; hi = pmax;
         sum = static_cast<int64_t>(sum_u) - (SG ? static_cast<int64_t>(count << 31) : 0);  // take the bias off: 2^31 per valid cell
     }
