@@ -563,11 +563,19 @@ def other_configs(ec, L, torch, dist, rank, world, barrier, max_over_ranks, peak
             r = evi()
             r.device_ptr()
         return r
+
+    def evi_jit():  # the same operators, chain compiled at run time into one streaming kernel (NVRTC build outside the timed calls)
+        with ec.lazy(jit=True):
+            r = evi()
+            r.device_ptr()
+        return r
     unfused_bytes = (2 + 2 + 8) + 16 + (2 + 8) + (2 + 8 + 8) + (2 + 8) + 24 + 16 + 24  # per cell, op by op
     res["extra_evi_u16_16384"] = {"unfused_8_ops": entry(timed(evi, 3, 1), float(unfused_bytes) * ne, ne),
                                   "lazy_expression_vm_1_pass": entry(timed(evi_lazy, 3, 1), 14.0 * ne, ne),
-                                  "note": "not a BASELINE config; the expression VM is opt-in (ec_set_lazy(2)): interpretation overhead eats the traffic it saves; "
-                                          "GB/s of the VM line = 14 B/cell (3 x u16 in, f64 out) / time"}
+                                  "lazy_specialised_kernel_1_pass": entry(timed(evi_jit, 3, 1), 14.0 * ne, ne, kernel=L.ec_last_kernel().decode()),
+                                  "note": "not a BASELINE config; both are opt-in: ec_set_lazy(2) = expression VM (interpretation overhead eats the traffic it saves), "
+                                          "ec_set_lazy(3) = kernel specialised at run time with NVRTC (falls back to op by op without libnvrtc); "
+                                          "GB/s of the 1-pass lines = 14 B/cell (3 x u16 in, f64 out) / time"}
     return res
 
 

@@ -13,13 +13,14 @@ ADD, SUB, MUL, DIV = 0, 1, 2, 3
 
 
 @_contextlib.contextmanager
-def lazy(on: bool = True, vm: bool = False):
+def lazy(on: bool = True, vm: bool = False, jit: bool = False):
     """Defer buffer arithmetic inside the block so that op chains fuse into single passes over HBM
     (`(a - b) / (a + b)`, `(a op b) op scalar`); results are bit-identical to eager evaluation.
-    vm=True also routes longer chains through the experimental expression VM (one interpreted pass)."""
+    jit=True compiles longer chains (e.g. EVI) into one kernel specialised at run time with NVRTC (cached by shape);
+    vm=True routes them through the experimental expression VM instead (one interpreted pass, slower)."""
     from ._lib import check, lib
     prev = lib().ec_get_lazy()
-    check(lib().ec_set_lazy((2 if vm else 1) if on else 0))
+    check(lib().ec_set_lazy((3 if jit else 2 if vm else 1) if on else 0))
     try:
         yield
     finally:

@@ -492,7 +492,7 @@ cudaError_t launch_binary_scalar(const Launch& L, int op1, int lct, const void* 
 //     (X op1 s1) op2 s2      -> one scale-and-offset kernel        (26 -> 10 B/cell for u16 * gain + offset)
 // Every op keeps its own IEEE rounding, so results are bit-identical to eager evaluation. Operands are
 // immutable snapshots: put/extend on a buffer that a pending Expr still references copy it first.
-static thread_local int t_lazy = 0;  // 0 eager, 1 deferred with the dedicated fused shapes, 2 also the expression VM
+static thread_local int t_lazy = 0;  // 0 eager, 1 deferred with the dedicated fused shapes, 2 also the expression VM, 3 also run-time specialised kernels
 enum : int { EX_BIN = 0, EX_SCALAR = 1 };
 struct Operand {
     uint8_t ct = 0;
@@ -603,6 +603,41 @@ static int vm_ops(const Expr& e) {  // number of ops the tree would fuse
     return n;
 }
 
+// ---- the same tree as the source of a run-time specialised kernel (ec_jit.cu), ec_set_lazy(3) ---------------------
+struct JitBuild {
+    JitProgram p;
+    int ops = 0;
+    bool ok = true;
+};
+static std::string jit_gen(JitBuild& b, Expr& e);
+static std::string jit_value(JitBuild& b, Operand& o) {
+    if (inlineable(o)) return jit_gen(b, *o.expr);
+    int k = 0;
+    for (; k < b.p.n_in; ++k)
+        if (b.p.in[k] == o.ptr && b.p.ct[k] == o.ct) break;
+    if (k == b.p.n_in) {
+        if (k == kJitInputs) { b.ok = false; return "v0"; }
+        b.p.in[k] = o.ptr;
+        b.p.ct[k] = o.ct;
+        ++b.p.n_in;
+    }
+    return "v" + std::to_string(k);
+}
+static std::string jit_gen(JitBuild& b, Expr& e) {
+    static const char* const fn[4] = {"ecj_add", "ecj_sub", "ecj_mul", "ecj_div"};
+    if (!b.ok || ++b.ops > kJitOps) { b.ok = false; return "v0"; }
+    const std::string l = jit_value(b, e.l);
+    std::string r;
+    if (e.kind == EX_SCALAR) {  // scalars are kernel parameters: one binary serves every value
+        if (b.p.n_const == kJitConsts) { b.ok = false; return "v0"; }
+        b.p.consts[b.p.n_const] = e.s;
+        r = "c" + std::to_string(b.p.n_const++);
+    } else {
+        r = jit_value(b, e.r);
+    }
+    return std::string(fn[e.op & 3]) + "(" + l + ", " + r + ")";
+}
+
 static ec_status eval_operand(Operand& o) {
     if (!o.expr) return EC_OK;
     if (ec_status s = eval(*o.expr)) return s;
@@ -634,7 +669,16 @@ static ec_status eval(Expr& e) {
         if (ec_status s = eval_operand(cl->r)) return s;
         err = launch_normdiff(launch_ctx(), cl->l.ct, cl->l.ptr, cl->r.ct, cl->r.ptr, static_cast<double*>(out), e.n);
         family = "normalized_difference(lazy)";
-    } else if (t_lazy >= 2 && vm_ops(e) >= 2 && [&] {  // opt-in: a longer chain as one interpreted pass (ec_vm.cuh)
+    } else if (t_lazy == 3 && vm_ops(e) >= 2 && [&] {  // opt-in: a longer chain as ONE kernel specialised at run time (ec_jit.cu)
+                   if (vm_prepare(e) != EC_OK) return false;
+                   JitBuild b;
+                   b.p.expr = jit_gen(b, e);
+                   if (!b.ok) return false;
+                   if (launch_jit(launch_ctx(), b.p, static_cast<double*>(out), e.n, &err) != 0) return false;  // no NVRTC here: op by op
+                   family = "expression_jit(lazy)";
+                   return true;
+               }()) {
+    } else if (t_lazy == 2 && vm_ops(e) >= 2 && [&] {  // opt-in: a longer chain as one interpreted pass (ec_vm.cuh)
                    if (vm_prepare(e) != EC_OK) return false;
                    VmBuild b;
                    vm_gen(b, e);
@@ -802,11 +846,29 @@ size_t ec_cached_bytes(void) {
 }
 uint64_t ec_guard_violations(void) { return g_guard_violations.load(); }
 ec_status ec_set_lazy(int mode) {
-    if (mode < 0 || mode > 2) return invalid("lazy mode");
+    if (mode < 0 || mode > 3) return invalid("lazy mode");
     t_lazy = mode;
     return EC_OK;
 }
 int ec_get_lazy(void) { return t_lazy; }
+size_t ec_jit_cached_kernels(void) { return jit_cached_kernels(); }
+ec_status ec_jit_dry_build(const uint8_t* cell_types, int n_in, int n_const, const char* expr, char* log, size_t log_capacity) {
+    if (n_in < 1 || n_in > kJitInputs || n_const < 0 || n_const > kJitConsts || !expr) return invalid("ec_jit_dry_build: operand / scalar count");
+    JitProgram p;
+    p.n_in = n_in;
+    p.n_const = n_const;
+    for (int k = 0; k < n_in; ++k) {
+        if (!ct_ok(cell_types[k])) return invalid("cell type");
+        p.ct[k] = cell_types[k];
+    }
+    p.expr = expr;
+    std::string source, text;
+    const int rc = jit_dry_build(p, &source, &text);
+    if (log && log_capacity) { strncpy(log, text.c_str(), log_capacity - 1); log[log_capacity - 1] = 0; }
+    if (rc == 1) { set_error("expression JIT unavailable: %s", text.c_str()); return EC_NO_DEVICE; }
+    if (rc != 0) { set_error("expression JIT: NVRTC build failed: %.900s", text.c_str()); return EC_INVALID_ARG; }
+    return EC_OK;
+}
 uint64_t ec_kernel_launches(void) { return g_launches.load(); }
 const char* ec_last_kernel(void) { return t_last_kernel; }
 ec_status ec_event_create(ec_event** out) {

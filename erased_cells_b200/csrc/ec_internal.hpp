@@ -77,6 +77,20 @@ cudaError_t launch_binary_scalar_static(const Launch& L, int op1, int lct, const
                                         double s, double* out, size_t n);
 cudaError_t launch_scalar_scalar(const Launch& L, int op1, int ct, const void* a, double s1, int op2, double s2, double* out, size_t n);
 cudaError_t launch_vm(const Launch& L, const VmProgram& p, double* out, size_t n);
+// run-time specialised kernel of one pending expression (ec_jit.cu): `expr` is straight-line C over v0.. (operands as
+// f64) and c0.. (scalars) built from ecj_add/sub/mul/div calls. Returns 0 = launched (*err = launch status),
+// 1 = not available (no NVRTC / build failed; ec_last_error says why) -> the caller evaluates op by op.
+constexpr int kJitInputs = 8, kJitConsts = 8, kJitOps = 48;
+struct JitProgram {
+    int n_in = 0, n_const = 0;
+    const void* in[kJitInputs] = {};
+    uint8_t ct[kJitInputs] = {};
+    double consts[kJitConsts] = {};
+    std::string expr;
+};
+int launch_jit(const Launch& L, const JitProgram& p, double* out, size_t n, cudaError_t* err);
+size_t jit_cached_kernels();
+int jit_dry_build(const JitProgram& p, std::string* source, std::string* log);
 // reductions: results land in scratch.result[0..1] (device); keys are unsigned order keys
 cudaError_t launch_min_max(const Launch& L, int ct, const void* a, const uint32_t* mask, size_t n,
                            const ReduceScratch& s);

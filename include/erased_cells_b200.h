@@ -217,9 +217,17 @@ ec_status ec_statistics_finish(const uint64_t* raws, size_t n_parts, const ec_va
  * `(X - Y) / (X + Y)`, `(X op1 Y) op2 scalar` and `(X op1 s1) op2 s2` into one pass over HBM. Results are bit-identical to eager
  * evaluation; later put/extend on an operand do not affect a pending result (copy on write).
  * ec_set_lazy(2) additionally sends longer chains through the expression VM (one interpreted pass, ec_vm.cuh) —
- * experimental: bit-identical, but measured only 1.1x faster than op-by-op evaluation on an 8-op chain. */
+ * experimental: bit-identical, but measured only 1.1x faster than op-by-op evaluation on an 8-op chain.
+ * ec_set_lazy(3) instead compiles such a chain (up to 8 operands, 8 scalars, 48 ops) into ONE streaming kernel
+ * specialised at run time with NVRTC (ec_jit.cu): same geometry, rounding and NaN rule as the eager kernels, cached
+ * by shape (scalars are kernel parameters). Without libnvrtc the chain is evaluated op by op (same bits). */
 ec_status ec_set_lazy(int mode);
 int ec_get_lazy(void);
+/* run-time specialised kernels built so far in this process */
+size_t ec_jit_cached_kernels(void);
+/* build (not load, not launch) the kernel for `expr` — straight-line C over v0.. (operands as f64) and c0.. (scalars)
+ * made of ecj_add/ecj_sub/ecj_mul/ecj_div calls — for sm_100a; works without a GPU. EC_NO_DEVICE = libnvrtc missing. */
+ec_status ec_jit_dry_build(const uint8_t* cell_types, int n_operands, int n_scalars, const char* expr, char* log, size_t log_capacity);
 /* `(&a - &b) / (&a + &b)` with the three roundings of the unfused chain; 1 pass over HBM */
 ec_status ec_buf_normalized_difference(const ec_buf* a, const ec_buf* b, ec_buf** out);
 /* `(l op1 r) op2 s`, e.g. README `buf1 / buf2 * 0.5` */

@@ -146,3 +146,28 @@ def test_device_calls_fail_loudly_without_gpu():
         ec.CellBuffer.from_vec(np.arange(4, dtype=np.uint8))
     with pytest.raises(ec.NoDeviceError):
         ec.Mask.fill(4, True)
+
+
+def test_jit_kernels_build_for_sm100a_without_a_gpu():
+    """ec_jit_dry_build: the run-time specialised kernel of a pending chain compiles with NVRTC for sm_100a (no load, no
+    launch). Skipped where libnvrtc cannot be loaded (the product then evaluates chains op by op)."""
+    import ctypes as C
+
+    import pytest
+
+    from erased_cells_b200 import _lib
+    L = _lib.lib()
+    log = C.create_string_buffer(4096)
+    evi = b"ecj_div(ecj_mul(ecj_sub(v0, v1), c0), ecj_add(ecj_sub(ecj_add(v0, ecj_mul(v1, c1)), ecj_mul(v2, c2)), c3))"
+    cts = (C.c_uint8 * 3)(1, 5, 0)
+    rc = L.ec_jit_dry_build(cts, 3, 4, evi, log, len(log))
+    if rc == _lib.EC_NO_DEVICE:
+        pytest.skip("libnvrtc not loadable here")
+    assert rc == _lib.EC_OK, log.value.decode()
+    for ct in range(10):  # every cell type as operand 0, eight operands of the widest type
+        cts = (C.c_uint8 * 2)(ct, 9 - ct)
+        assert L.ec_jit_dry_build(cts, 2, 1, b"ecj_mul(ecj_add(v0, v1), c0)", log, len(log)) == _lib.EC_OK, log.value.decode()
+    cts = (C.c_uint8 * 8)(*([9] * 8))
+    expr = b"ecj_add(ecj_add(ecj_add(v0, v1), ecj_add(v2, v3)), ecj_add(ecj_add(v4, v5), ecj_add(v6, v7)))"
+    assert L.ec_jit_dry_build(cts, 8, 0, expr, log, len(log)) == _lib.EC_OK, log.value.decode()
+    assert L.ec_jit_dry_build(cts, 2, 0, b"not_a_function(v0, v1)", log, len(log)) == _lib.EC_INVALID_ARG and b"not_a_function" in log.value

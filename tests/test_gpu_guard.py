@@ -29,7 +29,7 @@ SCRIPT = textwrap.dedent("""
             m = Mask.new(synth.host(CellType.UInt8, n, n) < 128)
             (~m); (m & m); (m | m); m.counts(); m.to_vec()
             ma = MaskedCellBuffer.from_buffer_with_nodata(a, NoData.default(ct))
-            (ma - MaskedCellBuffer(a, m)); ma.min_max(); MaskedCellBuffer(a, m).min_max()
+            (ma - MaskedCellBuffer(a, m)); ma.min_max(); MaskedCellBuffer(a, m).min_max(); a.statistics(); MaskedCellBuffer(a, m).statistics()
             for d in CellType:
                 if ct.can_fit_into(d):
                     a.convert(d); MaskedCellBuffer(a, m).to_vec_with_nodata(NoData.new(d, 1))

@@ -472,10 +472,10 @@ def test_lazy_expression_vm_matches_eager(orc):
         leaves = int(rng.integers(1, 7))
         f = build(int(rng.integers(2, 6)), leaves)
         e = f(dev)
-        for vm in (True, False):
-            with ec.lazy(vm=vm):
+        for mode in (dict(vm=True), dict(), dict(jit=True)):
+            with ec.lazy(**mode):
                 lz = f(dev)
-                assert lz == e, (trial, vm)            # device-side bitwise comparison forces the evaluation
+                assert lz == e, (trial, mode)          # device-side bitwise comparison forces the evaluation
     # shared sub-expression: evaluated once, used by two parents and by the user
     with ec.lazy(vm=True):
         num = dev[1] - dev[2]
@@ -491,6 +491,69 @@ def test_lazy_expression_vm_matches_eager(orc):
     y = dev[3]
     for i in range(60):
         y = y * 1.0001 + dev[4]
+    assert x == y
+
+
+def test_lazy_jit_specialised_kernels_match_eager(orc):
+    """ec.lazy(jit=True): a pending chain that no precompiled shape covers becomes ONE kernel specialised at run time
+    (NVRTC, ec_jit.cu) — bit-identical to eager evaluation and to the oracle, cached by shape with scalars as
+    parameters, ragged sizes, every cell type as an operand, shared sub-expressions, fallback past the size limits."""
+    L = ec.lib()
+    n = 3 * 32768 + 4099
+    types = list(CellType)
+    host = [cells(ct, n + (7 if i == 3 else 0), 0xA00 + i) for i, ct in enumerate(types)]
+    dev = [CellBuffer.from_vec(h) for h in host]
+    u8, u16, i16 = dev[int(CellType.UInt8)], dev[int(CellType.UInt16)], dev[int(CellType.Int16)]
+    h8, h16, hi16 = host[int(CellType.UInt8)], host[int(CellType.UInt16)], host[int(CellType.Int16)]
+    w = orc.tight_binary
+    s = lambda op, a, c: orc.tight_scalar(op, a, orc.value(orc.Float64, c))
+
+    def evi(nir, red, blue, g=2.5, c1=6.0, c2=7.5, l=1.0):
+        return ((nir - red) * g) / (((nir + red * c1) - blue * c2) + l)
+    eager = evi(u16, i16, u8)
+    with ec.lazy(jit=True):
+        k0, j0 = L.ec_kernel_launches(), L.ec_jit_cached_kernels()
+        got = evi(u16, i16, u8).to_vec()
+        if L.ec_last_kernel() != b"expression_jit(lazy)":
+            pytest.skip("libnvrtc not loadable on this box: chains fall back to op-by-op evaluation")
+        assert L.ec_kernel_launches() == k0 + 1 and L.ec_jit_cached_kernels() == j0 + 1
+        # other scalars, same shape: no new kernel
+        again = evi(u16, i16, u8, 2.4, 5.5, 7.0, 0.5).to_vec()
+        assert L.ec_jit_cached_kernels() == j0 + 1 and L.ec_kernel_launches() == k0 + 2
+    assert np.array_equal(bits(got), bits(eager.to_vec()))
+    want = w(orc.DIV, s(orc.MUL, w(orc.SUB, h16, hi16), 2.5), s(orc.ADD, w(orc.SUB, w(orc.ADD, h16, s(orc.MUL, hi16, 6.0)), s(orc.MUL, h8, 7.5)), 1.0))
+    assert np.array_equal(bits(got), bits(want))
+    assert np.array_equal(bits(again), bits(evi(u16, i16, u8, 2.4, 5.5, 7.0, 0.5).to_vec()))
+    # every cell type as an operand of a 3-op chain, all four ops, NaN/inf/-0.0/MIN/MAX specials included (cells())
+    for ct in types:
+        a, b = dev[int(ct)], dev[(int(ct) + 3) % 10]
+        ha, hb = host[int(ct)], host[(int(ct) + 3) % 10]
+        for op in range(4):
+            with ec.lazy(jit=True):
+                r = (a._bin(op, b) - a) / b
+                assert r.len() == n
+                got = r.to_vec()
+            want = w(orc.DIV, w(orc.SUB, w(op, ha, hb), ha), hb)
+            assert np.array_equal(bits(got), bits(want)), (ct, op)
+    # tiny and ragged sizes go through the scalar tail
+    for m in (1, 3, 5, 1023, 1025, 4097):
+        with ec.lazy(jit=True):
+            got = ((u16.view(0, m) + i16.view(0, m)) * 0.5 - u8.view(0, m)).to_vec()
+        assert np.array_equal(bits(got), bits(w(orc.SUB, s(orc.MUL, w(orc.ADD, h16[:m], hi16[:m]), 0.5), h8[:m])))
+    # a shared sub-expression is evaluated once and enters the kernel as an operand
+    with ec.lazy(jit=True):
+        num = u16 - i16
+        a = (num * 2.0 + u8) / (num - 1.0)
+        b = num / 3.0
+    assert a == ((u16 - i16) * 2.0 + u8) / ((u16 - i16) - 1.0) and b == (u16 - i16) / 3.0 and num == u16 - i16
+    # more than 8 scalars / 48 ops: falls back to op-by-op evaluation, same bits
+    with ec.lazy(jit=True):
+        x = dev[int(CellType.Float32)]
+        for i in range(60):
+            x = x * 1.0001 + dev[int(CellType.Float64)]
+    y = dev[int(CellType.Float32)]
+    for i in range(60):
+        y = y * 1.0001 + dev[int(CellType.Float64)]
     assert x == y
 
 
