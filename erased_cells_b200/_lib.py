@@ -90,6 +90,7 @@ def _signatures():
         "ec_set_lazy": (S, [I]),
         "ec_get_lazy": (I, []),
         "ec_jit_cached_kernels": (SZ, []),
+        "ec_jit_builds": (SZ, []),
         "ec_jit_dry_build": (S, [C.POINTER(U8), I, I, C.c_char_p, C.c_char_p, C.c_size_t]),
         "ec_kernel_launches": (U64, []),
         "ec_last_kernel": (C.c_char_p, []),

@@ -852,6 +852,7 @@ ec_status ec_set_lazy(int mode) {
 }
 int ec_get_lazy(void) { return t_lazy; }
 size_t ec_jit_cached_kernels(void) { return jit_cached_kernels(); }
+size_t ec_jit_builds(void) { return jit_builds(); }
 ec_status ec_jit_dry_build(const uint8_t* cell_types, int n_in, int n_const, const char* expr, char* log, size_t log_capacity) {
     if (n_in < 1 || n_in > kJitInputs || n_const < 0 || n_const > kJitConsts || !expr) return invalid("ec_jit_dry_build: operand / scalar count");
     JitProgram p;

@@ -90,6 +90,7 @@ struct JitProgram {
 };
 int launch_jit(const Launch& L, const JitProgram& p, double* out, size_t n, cudaError_t* err);
 size_t jit_cached_kernels();
+size_t jit_builds();
 int jit_dry_build(const JitProgram& p, std::string* source, std::string* log);
 // reductions: results land in scratch.result[0..1] (device); keys are unsigned order keys
 cudaError_t launch_min_max(const Launch& L, int ct, const void* a, const uint32_t* mask, size_t n,

@@ -144,7 +144,8 @@ inline CellValue max_value(CellType ct) { CellValue o; detail::check(ec_ctype_ma
 inline void set_lazy(bool on) { detail::check(ec_set_lazy(on ? 1 : 0)); }
 struct LazyScope {  // RAII: `{ LazyScope lazy; auto ndvi = (nir - red) / (nir + red); ... }`
     int prev;
-    LazyScope() : prev(ec_get_lazy()) { set_lazy(true); }
+    // mode 1: the precompiled fused shapes; 3: also kernels specialised at run time for longer chains (needs libnvrtc)
+    explicit LazyScope(int mode = 1) : prev(ec_get_lazy()) { detail::check(ec_set_lazy(mode)); }
     ~LazyScope() { ec_set_lazy(prev); }
     LazyScope(const LazyScope&) = delete;
     LazyScope& operator=(const LazyScope&) = delete;

@@ -225,6 +225,9 @@ ec_status ec_set_lazy(int mode);
 int ec_get_lazy(void);
 /* run-time specialised kernels built so far in this process */
 size_t ec_jit_cached_kernels(void);
+/* NVRTC builds done by this process; a kernel found in the on-disk cache ($EC_JIT_CACHE, default
+ * ~/.cache/erased_cells_b200/jit, "off" disables) is loaded without one */
+size_t ec_jit_builds(void);
 /* build (not load, not launch) the kernel for `expr` — straight-line C over v0.. (operands as f64) and c0.. (scalars)
  * made of ecj_add/ecj_sub/ecj_mul/ecj_div calls — for sm_100a; works without a GPU. EC_NO_DEVICE = libnvrtc missing. */
 ec_status ec_jit_dry_build(const uint8_t* cell_types, int n_operands, int n_scalars, const char* expr, char* log, size_t log_capacity);

@@ -6,6 +6,10 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# kernels specialised at run time (ec_set_lazy(3)) keep their cubins on disk: tests use a scratch directory, not ~/.cache
+import tempfile  # noqa: E402
+
+os.environ.setdefault("EC_JIT_CACHE", os.path.join(tempfile.gettempdir(), "erased_cells_b200_jit_tests"))
 
 
 def pytest_configure(config):

@@ -557,6 +557,34 @@ def test_lazy_jit_specialised_kernels_match_eager(orc):
     assert x == y
 
 
+def test_lazy_jit_cubins_persist_on_disk(tmp_path):
+    """a second process finds the built kernel in $EC_JIT_CACHE and runs it without an NVRTC build"""
+    import os
+    import subprocess
+    import sys
+    script = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import numpy as np, erased_cells_b200 as ec\n"
+        "from erased_cells_b200 import CellBuffer\n"
+        "a = CellBuffer.from_vec(np.arange(10000, dtype=np.uint16)); b = CellBuffer.from_vec(np.arange(10000, dtype=np.int32) - 77)\n"
+        "want = ((a - b) * 0.25 + a) / (b + 3.0)\n"
+        "with ec.lazy(jit=True):\n"
+        "    got = ((a - b) * 0.25 + a) / (b + 3.0)\n"
+        "    got.device_ptr(); kernel = ec.lib().ec_last_kernel().decode()\n"
+        "    same = got == want\n"
+        "print('RESULT', same, kernel, ec.lib().ec_jit_builds())\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, EC_JIT_CACHE=str(tmp_path / "jit"))
+    outs = [subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300, env=env) for _ in range(2)]
+    lines = [[l for l in o.stdout.splitlines() if l.startswith("RESULT")] for o in outs]
+    assert all(lines), outs[0].stderr[-2000:] + outs[1].stderr[-2000:]
+    first, second = lines[0][0].split(), lines[1][0].split()
+    if first[2] != "expression_jit(lazy)":
+        pytest.skip("libnvrtc not loadable on this box")
+    assert first[1] == "True" and first[3] == "1"
+    assert second[1:] == ["True", "expression_jit(lazy)", "0"] and len(list((tmp_path / "jit").glob("*.cubin"))) == 1
+
+
 def test_views_share_the_allocation(orc):
     """ec_buf_view: a strip of a resident raster as a buffer of its own — no copy, refcounted, copy on write."""
     n = 4 * 32768
