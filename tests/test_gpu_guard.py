@@ -37,6 +37,8 @@ SCRIPT = textwrap.dedent("""
             e = CellBuffer.from_vec(synth.host(ct, 40, 9)); e.extend(np.arange(5).astype(ct.dtype))
             with ec.lazy():
                 ((a - b) / (a + b)).to_vec(); (a / b * 0.5).to_vec()
+            with ec.lazy(jit=True):  # run-time specialised kernel (one build per cell type, then cached)
+                ((a - b) * 0.5 + a).to_vec()
     del a, b, m, ma, e
     L.ec_synchronize()
     print("launches", L.ec_kernel_launches() - launches0, "violations", L.ec_guard_violations())
