@@ -161,3 +161,38 @@ def test_config5_ndvi_u16_32768_tile(orc):
         hn, hr = synth.host(T.UInt16, WIN, 0xEC50, index_offset=off, **kw), synth.host(T.UInt16, WIN, 0xEC58, index_offset=off, **kw)
         want = orc.tight_binary(orc.DIV, orc.tight_binary(orc.SUB, hn, hr), orc.tight_binary(orc.ADD, hn, hr))
         assert np.array_equal(bits(window(fused, off, WIN)), bits(want))
+
+
+def test_more_than_2_pow_32_cells(orc):
+    """Maximum sizes: 2^32 + 4099 u8 cells (4.3 GB) — 64-bit cell indices everywhere. convert / binary are checked on
+    windows that straddle the 2^32 boundary and end at the last (ragged) cell; min_max, counts and statistics over the
+    whole buffer must equal what three unequal views (one across the boundary) combine to."""
+    n = (1 << 32) + 4099
+    a = synth.device(T.UInt8, n, 0xEC99, kind=synth.INT_RANGE, lo=1, hi=250, period=1 << 20, sentinel=0)
+    assert a.len() == n
+    wide = a.convert(T.UInt16)                       # 8.6 GB written
+    assert wide.len() == n and wide.cell_type() == T.UInt16
+    for off in (0, (1 << 32) - WIN // 2 - ((1 << 32) - WIN // 2) % 128, ((n - WIN) // 128) * 128):
+        m = min(WIN, n - off)
+        want = synth.host(T.UInt8, m, 0xEC99, index_offset=off, kind=synth.INT_RANGE, lo=1, hi=250, period=1 << 20, sentinel=0)
+        assert np.array_equal(window(a, off, m), want), off
+        assert np.array_equal(window(wide, off, m), want.astype(np.uint16)), off
+    tail = n - ((n - WIN) // 128) * 128
+    assert np.array_equal(wide.view(n - tail, tail).to_vec()[-5:], synth.host(T.UInt8, 5, 0xEC99, index_offset=n - 5, kind=synth.INT_RANGE, lo=1, hi=250,
+                                                                           period=1 << 20, sentinel=0).astype(np.uint16))
+    del wide
+    mn, mx = a.min_max()
+    assert (mn.value(), mx.value()) == (0, 250)
+    masked = MaskedCellBuffer.from_buffer_with_nodata(a, NoData.new(T.UInt8, 0))
+    data, nodata = masked.counts()
+    assert data + nodata == n and 0 < nodata < n // (1 << 19)
+    st, mst = a.statistics(), masked.statistics()
+    assert st.count == n and mst.count == data and mst.min.value() == 1
+    cuts = [0, (1 << 31) + 128 * 7, (1 << 32) + 128 * 3, n]  # the middle view starts below and ends above 2^32
+    kind, p, e = sharding.statistics_plan(st.min, st.max)
+    raws = [sharding.moments(a.view(i, j - i), None, p, e) for i, j in zip(cuts[:-1], cuts[1:])]
+    again = sharding.finish_statistics(raws, st.min, st.max)
+    assert (again.count, again.mean, again.stddev) == (st.count, st.mean, st.stddev)
+    assert abs(st.mean - 125.5) < 0.01 and abs(mst.mean - 125.5) < 0.01  # uniform 1..250 (+ a few zeros)
+    part_mm = [a.view(i, j - i).min_max() for i, j in zip(cuts[:-1], cuts[1:])]
+    assert min(v[0].value() for v in part_mm) == 0 and max(v[1].value() for v in part_mm) == 250
