@@ -88,6 +88,7 @@ def _signatures():
         "ec_guard_violations": (U64, []),
         "ec_cached_bytes": (SZ, []),
         "ec_set_lazy": (S, [I]),
+        "ec_set_launch_overlap": (I, [I]),
         "ec_get_lazy": (I, []),
         "ec_jit_cached_kernels": (SZ, []),
         "ec_jit_builds": (SZ, []),

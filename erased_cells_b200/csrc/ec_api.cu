@@ -71,6 +71,7 @@ struct Ctx {
     cudaStream_t upload = nullptr;  // H2D of ec_buf_from_host_async: overlaps the D2H traffic of the compute stream
     cudaDeviceProp prop;
     int max_grid = 0;
+    std::atomic<int> overlap{1};  // programmatic dependent launch of the streaming kernels (EC_LAUNCH_OVERLAP, ec_set_launch_overlap)
 };
 static Ctx g_ctx;
 static thread_local cudaStream_t t_stream = nullptr;
@@ -103,7 +104,9 @@ static inline void* rd(const ec_buf* b) {
     if (b->ready) cudaStreamWaitEvent(cur_stream(), b->ready, 0);
     return b->dptr;
 }
-static Launch launch_ctx() { return Launch{cur_stream(), g_ctx.prop.multiProcessorCount, g_ctx.max_grid}; }
+static Launch launch_ctx() {
+    return Launch{cur_stream(), g_ctx.prop.multiProcessorCount, g_ctx.max_grid, g_ctx.overlap.load(std::memory_order_relaxed) != 0};
+}
 
 // ---- device memory: a stream-keyed caching allocator --------------------------------------------
 // Every op returns a fresh buffer, so allocation sits on the hot path. cudaMallocAsync's pool re-maps
@@ -804,6 +807,7 @@ ec_status ec_init(int device) {
     EC_CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.own, cudaStreamNonBlocking), "cudaStreamCreate");
     EC_CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.upload, cudaStreamNonBlocking), "cudaStreamCreate");
     g_ctx.max_grid = env_int("EC_MAX_GRID", 0);
+    g_ctx.overlap = env_int("EC_LAUNCH_OVERLAP", 1) != 0 && g_ctx.prop.major >= 9;
     g_guard = env_int("EC_DEBUG_GUARD", 0) != 0;
     g_ctx.device = device;
     g_ctx.inited = true;
@@ -851,6 +855,10 @@ ec_status ec_set_lazy(int mode) {
     return EC_OK;
 }
 int ec_get_lazy(void) { return t_lazy; }
+int ec_set_launch_overlap(int on) {
+    if (ensure() != EC_OK) return -1;
+    return g_ctx.overlap.exchange(on != 0 && g_ctx.prop.major >= 9);
+}
 size_t ec_jit_cached_kernels(void) { return jit_cached_kernels(); }
 size_t ec_jit_builds(void) { return jit_builds(); }
 ec_status ec_jit_dry_build(const uint8_t* cell_types, int n_in, int n_const, const char* expr, char* log, size_t log_capacity) {

@@ -43,6 +43,7 @@ struct Launch {  // launch context handed to every launcher
     cudaStream_t stream;
     int sm_count;
     int max_grid;  // cap for the persistent grids (<= 0: one tile per CTA)
+    bool overlap;  // programmatic dependent launch: the grid may be scheduled while its predecessor drains
 };
 
 void set_error(const char* fmt, ...);
@@ -57,6 +58,24 @@ inline int grid_for(size_t n, size_t tile, const Launch& L) {
     size_t cap = L.max_grid > 0 ? size_t(L.max_grid) : (size_t(1) << 30);
     return int(full < cap ? full : cap);
 }
+
+// Launch of a kernel whose first statement is overlap_prologue() (ec_common.cuh). With L.overlap the grid carries the
+// programmatic-stream-serialization attribute; memory ordering against the previous grid is kept by the prologue.
+#ifdef __CUDACC__
+template <class... P, class... A>
+inline cudaError_t launch_k(const Launch& L, void (*kernel)(P...), int grid, int threads, A&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(unsigned(grid));
+    cfg.blockDim = dim3(unsigned(threads));
+    cfg.stream = L.stream;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = L.overlap ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<A&&>(args)...);
+}
+#endif
 
 // ---- launchers (each TU instantiates its kernel family) ----------------------------------------
 // binary: out[i] = (f64)l[i] op (f64)r[i]; optional fused mask AND

@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(THREADS) map1_kernel(const typename F::A* __re
     constexpr int V = VB / cmax<sizeof(A), sizeof(O)>();
     constexpr size_t TILE = size_t(THREADS) * V * UNROLL;
     const size_t full = n / TILE;
+    overlap_prologue();
     for (size_t t = blockIdx.x; t < full; t += gridDim.x) {
         const size_t base = t * TILE + size_t(threadIdx.x) * V;
         Vec<A, V> va[UNROLL];
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(THREADS, map2_min_ctas<F>(THREADS)) map2_kerne
     static_assert(TILE % 128 == 0, "a tile must cover whole 16-byte groups of mask words");
     constexpr int TILE_WORDS = TILE / 32;
     const size_t full = n / TILE;
+    overlap_prologue();
     for (size_t t = blockIdx.x; t < full; t += gridDim.x) {
         const size_t base = t * TILE + size_t(threadIdx.x) * V;
         Vec<A, V> va[UNROLL];
@@ -169,6 +171,7 @@ __global__ void __launch_bounds__(THREADS) fill_kernel(T* __restrict__ o, size_t
 #pragma unroll
     for (int j = 0; j < V; ++j) vv.v[j] = value;
     const size_t full = n / TILE;
+    overlap_prologue();
     for (size_t t = blockIdx.x; t < full; t += gridDim.x) st_stream<T, V>(o + t * TILE + size_t(threadIdx.x) * V, vv);
     if (blockIdx.x == full % gridDim.x)
         for (size_t i = full * TILE + threadIdx.x; i < n; i += THREADS) o[i] = value;
@@ -184,6 +187,7 @@ __global__ void __launch_bounds__(THREADS) fill_nodata_kernel(const S* __restric
     constexpr size_t TILE = size_t(THREADS) * V * UNROLL;
     constexpr uint32_t VMASK = V == 32 ? 0xFFFFFFFFu : ((1u << V) - 1u);
     const size_t full = n / TILE;
+    overlap_prologue();
     for (size_t t = blockIdx.x; t < full; t += gridDim.x) {
         const size_t base = t * TILE + size_t(threadIdx.x) * V;
         Vec<S, V> va[UNROLL];

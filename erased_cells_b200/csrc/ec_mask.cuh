@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(THREADS) mask_build_kernel(const U* __restrict
     constexpr size_t TILE = size_t(THREADS) * V * UNROLL;
     const int lane = threadIdx.x & 31;
     const size_t full = n / TILE;
+    overlap_prologue();
     for (size_t t = blockIdx.x; t < full; t += gridDim.x) {
         const size_t base = t * TILE + size_t(threadIdx.x) * V;
         Vec<U, V> va[UNROLL];
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(THREADS) mask_bitop_kernel(int mop, const uint
                                                              uint32_t* __restrict__ out) {
     const size_t words = (n + 31) / 32;
     const size_t groups = words / 4;
+    overlap_prologue();
     for (size_t g = blockIdx.x * size_t(THREADS) + threadIdx.x; g < groups; g += size_t(gridDim.x) * THREADS) {
         Vec<uint32_t, 4> x = ld_stream<uint32_t, 4>(l + 4 * g), y = x, o;
         if (mop != MOP_NOT) y = ld_stream<uint32_t, 4>(r + 4 * g);
@@ -123,6 +125,7 @@ __global__ void __launch_bounds__(THREADS) mask_bitop_kernel(int mop, const uint
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) mask_fill_kernel(uint32_t* __restrict__ out, size_t n, uint32_t word) {
     const size_t words = (n + 31) / 32;
+    overlap_prologue();
     for (size_t w = blockIdx.x * size_t(THREADS) + threadIdx.x; w < words; w += size_t(gridDim.x) * THREADS) {
         uint32_t v = word;
         if (w == words - 1 && (n % 32) != 0) v &= (1u << (n % 32)) - 1u;

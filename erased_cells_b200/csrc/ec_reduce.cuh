@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(THREADS) min_max_kernel(const T* __restrict__ 
     constexpr size_t TILE = size_t(THREADS) * V * UNROLL;
     const size_t full = n / TILE;
     K kmin = seed_min, kmax = seed_max;
+    overlap_prologue();
 
     if constexpr (MASKED && sizeof(T) == 1 && VB == 32) {
         // 8-bit cells with a mask: a thread's 32 cells are exactly one mask word. Invalid bytes are forced to the
@@ -286,6 +287,7 @@ __global__ void __launch_bounds__(THREADS) popcount_kernel(const uint32_t* __res
                                                            uint64_t second_word) {
     uint64_t c = 0;
     const size_t groups = words / 4;  // 16-byte groups (allocation is padded to 16 bytes, pad is zero)
+    overlap_prologue();
     for (size_t g = blockIdx.x * size_t(THREADS) + threadIdx.x; g < groups; g += size_t(gridDim.x) * THREADS) {
         const Vec<uint32_t, 4> w = ld_stream<uint32_t, 4>(m + 4 * g);
         c += __popc(w.v[0]) + __popc(w.v[1]) + __popc(w.v[2]) + __popc(w.v[3]);
@@ -303,6 +305,7 @@ __global__ void __launch_bounds__(THREADS) first_diff_kernel(const T* __restrict
     constexpr int V = VB / sizeof(T);
     uint64_t first = ~0ull;
     const size_t groups = n / V;
+    overlap_prologue();
     // compare 32 bytes as four 64-bit words; only a differing word is examined cell by cell (lowest differing byte)
     for (size_t g = blockIdx.x * size_t(THREADS) + threadIdx.x; g < groups; g += size_t(gridDim.x) * THREADS) {
         const Raw<VB> x = ld_stream_raw<VB>(a + g * V), y = ld_stream_raw<VB>(b + g * V);

@@ -22,8 +22,7 @@ static cudaError_t go2(const Launch& Lc, const typename F::A* l, const typename 
                        const uint32_t* lm, const uint32_t* rm, uint32_t* om) {
     constexpr int V = EC_VB / cmax<cmax<sizeof(typename F::A), sizeof(typename F::B)>(), sizeof(double)>();
     constexpr size_t TILE = size_t(kThreads) * V * EC_UNROLL;
-    map2_kernel<F, EC_VB, EC_UNROLL, kThreads><<<grid_for(n, TILE, Lc), kThreads, 0, Lc.stream>>>(l, r, out, n, f, lm, rm, om);
-    return cudaGetLastError();
+    return launch_k(Lc, map2_kernel<F, EC_VB, EC_UNROLL, kThreads>, grid_for(n, TILE, Lc), kThreads, l, r, out, n, f, lm, rm, om);
 }
 
 template <class R>

@@ -19,9 +19,8 @@ static cudaError_t go(const Launch& Lc, const void* l, const void* r, double s, 
     using F = BinaryScalarT<L, R, OP1, OP2>;
     constexpr int V = EC_VB / cmax<cmax<sizeof(L), sizeof(R)>(), 8>();
     constexpr size_t TILE = size_t(kThreads) * V * EC_UNROLL;
-    map2_kernel<F, EC_VB, EC_UNROLL, kThreads><<<grid_for(n, TILE, Lc), kThreads, 0, Lc.stream>>>(
-        static_cast<const L*>(l), static_cast<const R*>(r), out, n, F{s}, nullptr, nullptr, nullptr);
-    return cudaGetLastError();
+    return launch_k(Lc, map2_kernel<F, EC_VB, EC_UNROLL, kThreads>, grid_for(n, TILE, Lc), kThreads,
+                    static_cast<const L*>(l), static_cast<const R*>(r), out, n, F{s}, nullptr, nullptr, nullptr);
 }
 template <class L, class R, int OP1>
 static cudaError_t by_op2(const Launch& Lc, int op2, const void* l, const void* r, double s, double* out, size_t n) {
@@ -61,8 +60,7 @@ static cudaError_t go_ss(const Launch& Lc, const void* a, double s1, double s2, 
     using F = ScalarScalarT<L, OP1, OP2>;
     constexpr int V = EC_VB / cmax<sizeof(L), 8>();
     constexpr size_t TILE = size_t(kThreads) * V * EC_UNROLL;
-    map1_kernel<F, EC_VB, EC_UNROLL, kThreads><<<grid_for(n, TILE, Lc), kThreads, 0, Lc.stream>>>(static_cast<const L*>(a), out, n, F{s1, s2});
-    return cudaGetLastError();
+    return launch_k(Lc, map1_kernel<F, EC_VB, EC_UNROLL, kThreads>, grid_for(n, TILE, Lc), kThreads, static_cast<const L*>(a), out, n, F{s1, s2});
 }
 template <class L, int OP1> static cudaError_t ss_op2(const Launch& Lc, int op2, const void* a, double s1, double s2, double* out, size_t n) {
     switch (op2) {

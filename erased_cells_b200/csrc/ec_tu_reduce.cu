@@ -41,14 +41,13 @@ static cudaError_t min_max_t(const Launch& Lc, const void* a, const uint32_t* ma
     const okey_t<T> smin = to_key<T>(std::numeric_limits<T>::max()), smax = to_key<T>(std::numeric_limits<T>::lowest());
     if (mask) {
         constexpr size_t TILE = size_t(kRedThreadsMasked) * V * kRedUnrollMasked;
-        min_max_kernel<T, true, EC_VB, kRedUnrollMasked, kRedThreadsMasked><<<reduce_grid(n, TILE, Lc, kRedCtasPerSmMasked), kRedThreadsMasked, 0, Lc.stream>>>(
-            static_cast<const T*>(a), mask, n, smin, smax, s);
+        return launch_k(Lc, min_max_kernel<T, true, EC_VB, kRedUnrollMasked, kRedThreadsMasked>, reduce_grid(n, TILE, Lc, kRedCtasPerSmMasked),
+                        kRedThreadsMasked, static_cast<const T*>(a), mask, n, smin, smax, s);
     } else {
         constexpr size_t TILE = size_t(kRedThreads) * V * kRedUnroll;
-        min_max_kernel<T, false, EC_VB, kRedUnroll, kRedThreads><<<reduce_grid(n, TILE, Lc, kRedCtasPerSm), kRedThreads, 0, Lc.stream>>>(
-            static_cast<const T*>(a), nullptr, n, smin, smax, s);
+        return launch_k(Lc, min_max_kernel<T, false, EC_VB, kRedUnroll, kRedThreads>, reduce_grid(n, TILE, Lc, kRedCtasPerSm), kRedThreads,
+                        static_cast<const T*>(a), nullptr, n, smin, smax, s);
     }
-    return cudaGetLastError();
 }
 cudaError_t launch_min_max(const Launch& Lc, int ct, const void* a, const uint32_t* mask, size_t n, const ReduceScratch& s) {
     switch (ct) {
@@ -86,14 +85,12 @@ uint64_t key_from_signed(int64_t skey) { return static_cast<uint64_t>(skey) ^ 0x
 
 cudaError_t launch_popcount(const Launch& Lc, const uint32_t* words, size_t nwords, const ReduceScratch& s, uint64_t second_word) {
     const int grid = reduce_grid(nwords / 4, kThreads, Lc);
-    popcount_kernel<kThreads><<<grid, kThreads, 0, Lc.stream>>>(words, nwords, s, second_word);
-    return cudaGetLastError();
+    return launch_k(Lc, popcount_kernel<kThreads>, grid, kThreads, words, nwords, s, second_word);
 }
 
 template <class U> static cudaError_t first_diff_u(const Launch& Lc, const void* a, const void* b, size_t n, const ReduceScratch& s) {
     const int grid = reduce_grid(n / (EC_VB / sizeof(U)), kThreads, Lc);
-    first_diff_kernel<U, EC_VB, kThreads><<<grid, kThreads, 0, Lc.stream>>>(static_cast<const U*>(a), static_cast<const U*>(b), n, s);
-    return cudaGetLastError();
+    return launch_k(Lc, first_diff_kernel<U, EC_VB, kThreads>, grid, kThreads, static_cast<const U*>(a), static_cast<const U*>(b), n, s);
 }
 cudaError_t launch_first_diff(const Launch& Lc, int cell_bytes, const void* a, const void* b, size_t n, const ReduceScratch& s) {
     switch (cell_bytes) {
@@ -109,9 +106,8 @@ static cudaError_t mask_build_u(const Launch& Lc, const void* a, size_t n, uint6
     constexpr int V0 = EC_VB / sizeof(U);
     constexpr int V = V0 > 32 ? 32 : V0;
     constexpr size_t TILE = size_t(kThreads) * V * EC_RUNROLL;
-    mask_build_kernel<U, PACK, EC_VB, EC_RUNROLL, kThreads><<<grid_for(n, TILE, Lc), kThreads, 0, Lc.stream>>>(
-        static_cast<const U*>(a), n, static_cast<U>(sentinel), out);
-    return cudaGetLastError();
+    return launch_k(Lc, mask_build_kernel<U, PACK, EC_VB, EC_RUNROLL, kThreads>, grid_for(n, TILE, Lc), kThreads,
+                    static_cast<const U*>(a), n, static_cast<U>(sentinel), out);
 }
 cudaError_t launch_mask_build(const Launch& Lc, int cell_bytes, const void* a, size_t n, uint64_t sentinel_bits,
                               bool pack_bools, uint32_t* out) {
@@ -128,12 +124,10 @@ cudaError_t launch_mask_unpack(const Launch& Lc, const uint32_t* m, size_t n, ui
     return cudaGetLastError();
 }
 cudaError_t launch_mask_bitop(const Launch& Lc, int mop, const uint32_t* l, const uint32_t* r, size_t n, uint32_t* out) {
-    mask_bitop_kernel<kThreads><<<grid_for((n + 127) / 128, kThreads, Lc), kThreads, 0, Lc.stream>>>(mop, l, r, n, out);
-    return cudaGetLastError();
+    return launch_k(Lc, mask_bitop_kernel<kThreads>, grid_for((n + 127) / 128, kThreads, Lc), kThreads, mop, l, r, n, out);
 }
 cudaError_t launch_mask_fill(const Launch& Lc, uint32_t* out, size_t n, bool value) {
-    mask_fill_kernel<kThreads><<<grid_for((n + 31) / 32, kThreads, Lc), kThreads, 0, Lc.stream>>>(out, n, value ? 0xFFFFFFFFu : 0u);
-    return cudaGetLastError();
+    return launch_k(Lc, mask_fill_kernel<kThreads>, grid_for((n + 31) / 32, kThreads, Lc), kThreads, out, n, value ? 0xFFFFFFFFu : 0u);
 }
 
 // ---- Extend<C> (src/buffer.rs:205-221): value-checked cast `c.into_cell_value().to_<p>().unwrap()` ---------

@@ -15,8 +15,7 @@ template <class F>
 static cudaError_t go1(const Launch& Lc, const typename F::A* a, typename F::O* out, size_t n, F f) {
     constexpr int V = EC_VB / cmax<sizeof(typename F::A), sizeof(typename F::O)>();
     constexpr size_t TILE = size_t(kThreads) * V * EC_UNROLL;
-    map1_kernel<F, EC_VB, EC_UNROLL, kThreads><<<grid_for(n, TILE, Lc), kThreads, 0, Lc.stream>>>(a, out, n, f);
-    return cudaGetLastError();
+    return launch_k(Lc, map1_kernel<F, EC_VB, EC_UNROLL, kThreads>, grid_for(n, TILE, Lc), kThreads, a, out, n, f);
 }
 
 cudaError_t launch_scalar(const Launch& Lc, int op, int lct, const void* l, double s, double* out, size_t n) {
@@ -72,8 +71,7 @@ cudaError_t launch_copy(const Launch& Lc, int cell_bytes, const void* a, void* o
 
 template <class U> static cudaError_t fill_u(const Launch& Lc, void* out, size_t n, uint64_t bits) {
     constexpr size_t TILE = size_t(kThreads) * (EC_VB / sizeof(U));
-    fill_kernel<U, EC_VB, kThreads><<<grid_for(n, TILE, Lc), kThreads, 0, Lc.stream>>>(static_cast<U*>(out), n, static_cast<U>(bits));
-    return cudaGetLastError();
+    return launch_k(Lc, fill_kernel<U, EC_VB, kThreads>, grid_for(n, TILE, Lc), kThreads, static_cast<U*>(out), n, static_cast<U>(bits));
 }
 cudaError_t launch_fill(const Launch& Lc, int ct, void* out, size_t n, uint64_t bits) {
     static const int sz[CT_COUNT] = {1, 2, 4, 8, 1, 2, 4, 8, 4, 8};
@@ -91,9 +89,8 @@ static cudaError_t fill_nd(const Launch& Lc, const void* a, const uint32_t* m, v
     constexpr int V = V0 > 32 ? 32 : V0;
     constexpr size_t TILE = size_t(kThreads) * V * EC_UNROLL;
     const D nd = from_bits<D>(static_cast<bits_t<D>>(nd_bits));
-    fill_nodata_kernel<S, D, EC_VB, EC_UNROLL, kThreads><<<grid_for(n, TILE, Lc), kThreads, 0, Lc.stream>>>(
-        static_cast<const S*>(a), m, static_cast<D*>(out), n, nd);
-    return cudaGetLastError();
+    return launch_k(Lc, fill_nodata_kernel<S, D, EC_VB, EC_UNROLL, kThreads>, grid_for(n, TILE, Lc), kThreads,
+                    static_cast<const S*>(a), m, static_cast<D*>(out), n, nd);
 }
 cudaError_t launch_fill_nodata(const Launch& Lc, int sct, const void* a, const uint32_t* m, int dct, void* out, size_t n,
                                uint64_t nodata_bits) {

@@ -223,6 +223,13 @@ ec_status ec_statistics_finish(const uint64_t* raws, size_t n_parts, const ec_va
  * by shape (scalars are kernel parameters). Without libnvrtc the chain is evaluated op by op (same bits). */
 ec_status ec_set_lazy(int mode);
 int ec_get_lazy(void);
+/* Launch overlap (process-wide, default on; EC_LAUNCH_OVERLAP=0 turns it off at ec_init): every op of the reference's
+ * API is its own kernel launch, so a chain or a sweep pays the drain of one grid plus the ramp of the next per op.
+ * With overlap on, the streaming kernels are launched with programmatic stream serialization (sm_90+): a grid's
+ * CTAs may be scheduled while the grid before it on the stream drains, and block on `griddepcontrol.wait` — until
+ * that grid has completed and its writes are visible — before their first global memory access. Stream order of
+ * every read and write is unchanged, results are identical. Returns the previous setting, -1 without a device. */
+int ec_set_launch_overlap(int on);
 /* run-time specialised kernels built so far in this process */
 size_t ec_jit_cached_kernels(void);
 /* NVRTC builds done by this process; a kernel found in the on-disk cache ($EC_JIT_CACHE, default
