@@ -151,6 +151,10 @@ struct LazyScope {  // RAII: `{ LazyScope lazy; auto ndvi = (nir - red) / (nir +
     LazyScope& operator=(const LazyScope&) = delete;
 };
 
+// Launch overlap (process-wide, on by default): a kernel's CTAs are scheduled while the previous op's grid drains
+// (programmatic dependent launch); results are identical either way. Returns the previous setting.
+inline bool set_launch_overlap(bool on) { return ec_set_launch_overlap(on ? 1 : 0) == 1; }
+
 // ---- CellBuffer — src/buffer.rs; BufferOps — src/lib.rs:104-163 -----------------------------------------------
 // count / min / max / mean / population stddev of the valid cells — an extension (ec_statistics): the reference has no
 // statistics beyond min_max and Mask::counts. Order-independent definition, see DESIGN.md §4.6.

@@ -112,7 +112,8 @@ def full():
         open(os.path.join(P, dst + "_raw.csv"), "w").write("".join(l for l in open(path) if l.strip() and not l.startswith("==")))
 
 
-ubench()
-launch_list()
-full()
-print(os.listdir(P))
+if __name__ == '__main__':
+    only = sys.argv[2:] or ['ubench', 'launch_list', 'full']
+    for name in only:
+        globals()[name]()
+    print(os.listdir(P))
