@@ -1035,6 +1035,14 @@ ec_status ec_value_to_prim(const ec_value* v, uint8_t ct, ec_value* out, int* is
 }
 
 // ---- CellBuffer --------------------------------------------------------------------------------------
+struct BufOwner {  // a half-built result: an early error return frees it
+    ec_buf* b = nullptr;
+    BufOwner() = default;
+    BufOwner(const BufOwner&) = delete;
+    BufOwner& operator=(const BufOwner&) = delete;
+    ~BufOwner() { if (b) ec_buf_free(b); }
+    ec_buf* release() { ec_buf* q = b; b = nullptr; return q; }
+};
 ec_status ec_buf_from_host(uint8_t ct, const void* host, size_t len, ec_buf** out) {
     EC_TRY(ensure());
     if (!ct_ok(ct)) return invalid("cell type");
@@ -1052,20 +1060,18 @@ ec_status ec_buf_from_host(uint8_t ct, const void* host, size_t len, ec_buf** ou
 ec_status ec_buf_from_host_async(uint8_t ct, const void* host, size_t len, ec_buf** out) {
     EC_TRY(ensure());
     if (!ct_ok(ct)) return invalid("cell type");
-    ec_buf* b;
-    EC_TRY(new_buf(ct, len, &b));
+    BufOwner o;
+    EC_TRY(new_buf(ct, len, &o.b));
+    ec_buf* b = o.b;
     if (len) {
         EC_CUDA_TRY(cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming), "cudaEventCreate");
         // the block may have been recycled from work still queued on the current stream: upload after it
         EC_CUDA_TRY(cudaEventRecord(b->ready, cur_stream()), "cudaEventRecord");
         EC_CUDA_TRY(cudaStreamWaitEvent(g_ctx.upload, b->ready, 0), "cudaStreamWaitEvent");
-        if (cudaError_t e = cudaMemcpyAsync(b->dptr, host, len * kSize[ct], cudaMemcpyHostToDevice, g_ctx.upload)) {
-            ec_buf_free(b);
-            return cuda_fail(e, "cudaMemcpyAsync(H2D)");
-        }
+        EC_CUDA_TRY(cudaMemcpyAsync(b->dptr, host, len * kSize[ct], cudaMemcpyHostToDevice, g_ctx.upload), "cudaMemcpyAsync(H2D)");
         EC_CUDA_TRY(cudaEventRecord(b->ready, g_ctx.upload), "cudaEventRecord");
     }
-    *out = b;
+    *out = o.release();
     return EC_OK;
 }
 ec_status ec_buf_wait(const ec_buf* b) {
@@ -1076,19 +1082,19 @@ ec_status ec_buf_wait(const ec_buf* b) {
 ec_status ec_buf_with_defaults(size_t len, uint8_t ct, ec_buf** out) {
     EC_TRY(ensure());
     if (!ct_ok(ct)) return invalid("cell type");
-    ec_buf* b;
-    EC_TRY(new_buf(ct, len, &b));
-    if (len) EC_CUDA_TRY(cudaMemsetAsync(b->dptr, 0, len * kSize[ct], cur_stream()), "cudaMemsetAsync");
-    *out = b;
+    BufOwner o;
+    EC_TRY(new_buf(ct, len, &o.b));
+    if (len) EC_CUDA_TRY(cudaMemsetAsync(o.b->dptr, 0, len * kSize[ct], cur_stream()), "cudaMemsetAsync");
+    *out = o.release();
     return EC_OK;
 }
 ec_status ec_buf_fill(size_t len, const ec_value* value, ec_buf** out) {
     EC_TRY(ensure());
     if (!ct_ok(value->ct)) return invalid("cell type");
-    ec_buf* b;
-    EC_TRY(new_buf(value->ct, len, &b));
-    if (len) EC_LAUNCH(launch_fill(launch_ctx(), b->ct, b->dptr, len, value->bits), "fill");
-    *out = b;
+    BufOwner o;
+    EC_TRY(new_buf(value->ct, len, &o.b));
+    if (len) EC_LAUNCH(launch_fill(launch_ctx(), o.b->ct, o.b->dptr, len, value->bits), "fill");
+    *out = o.release();
     return EC_OK;
 }
 ec_status ec_buf_wrap_device(uint8_t ct, void* device_ptr, size_t len, ec_buf** out) {
@@ -1483,11 +1489,12 @@ ec_status ec_buf_binary_scalar(int op1, const ec_buf* l, const ec_buf* r, int op
 }
 
 // ---- Mask ------------------------------------------------------------------------------------------------
+using MaskOwner = std::unique_ptr<ec_mask, void (*)(ec_mask*)>;  // a half-built result: an early error return frees it
 ec_status ec_mask_from_bools(const uint8_t* host_bools, size_t len, ec_mask** out) {
     EC_TRY(ensure());
     ec_mask* m;
     EC_TRY(new_mask(len, &m));
-    std::unique_ptr<ec_mask, void (*)(ec_mask*)> hold(m, ec_mask_free);
+    MaskOwner hold(m, ec_mask_free);
     if (len) {
         Scratch stage;
         EC_TRY(stage.alloc(len));
@@ -1501,8 +1508,9 @@ ec_status ec_mask_fill(size_t len, int value, ec_mask** out) {
     EC_TRY(ensure());
     ec_mask* m;
     EC_TRY(new_mask(len, &m));
+    MaskOwner hold(m, ec_mask_free);
     if (len) EC_LAUNCH(launch_mask_fill(launch_ctx(), m->words, len, value != 0), "mask_fill");
-    *out = m;
+    *out = hold.release();
     return EC_OK;
 }
 ec_status ec_mask_to_bools(const ec_mask* m, uint8_t* host_bools, size_t capacity) {
@@ -1519,8 +1527,9 @@ ec_status ec_mask_clone(const ec_mask* m, ec_mask** out) {
     EC_TRY(ensure());
     ec_mask* c;
     EC_TRY(new_mask(m->len, &c));
+    MaskOwner hold(c, ec_mask_free);
     if (m->len) EC_CUDA_TRY(cudaMemcpyAsync(c->words, m->words, ((m->len + 31) / 32) * 4, cudaMemcpyDeviceToDevice, cur_stream()), "cudaMemcpyAsync(D2D)");
-    *out = c;
+    *out = hold.release();
     return EC_OK;
 }
 void ec_mask_free(ec_mask* m) {
@@ -1582,8 +1591,9 @@ static ec_status mask_bitop(int mop, const ec_mask* l, const ec_mask* r, ec_mask
     const size_t n = r ? std::min(l->len, r->len) : l->len;  // zip (src/masked/mask.rs:133-137)
     ec_mask* o;
     EC_TRY(new_mask(n, &o));
+    MaskOwner hold(o, ec_mask_free);
     if (n) EC_LAUNCH(launch_mask_bitop(launch_ctx(), mop, l->words, r ? r->words : nullptr, n, o->words), "mask_bitop");
-    *out = o;
+    *out = hold.release();
     return EC_OK;
 }
 ec_status ec_mask_not(const ec_mask* m, ec_mask** out) { return mask_bitop(0, m, nullptr, out); }
@@ -1649,8 +1659,9 @@ ec_status ec_mask_from_nodata(const ec_buf* b, int kind, const ec_value* v, ec_m
     EC_TRY(resolve(b));
     ec_mask* m;
     EC_TRY(new_mask(b->len, &m));
+    MaskOwner hold(m, ec_mask_free);
     if (b->len) EC_LAUNCH(launch_mask_build(launch_ctx(), (int)kSize[b->ct], rd(b), b->len, nd.bits, false, m->words), "mask_from_nodata");
-    *out = m;
+    *out = hold.release();
     return EC_OK;
 }
 ec_status ec_buf_fill_nodata(const ec_buf* b, const ec_mask* m, uint8_t dst_ct, int kind, const ec_value* v, ec_buf** out) {
@@ -1679,7 +1690,11 @@ ec_status ec_masked_binary(int op, const ec_buf* lbuf, const ec_mask* lmask, con
     const size_t n = std::min(lbuf->len, rbuf->len);
     ec_mask* om;
     EC_TRY(new_mask(n, &om));
-    if (n == 0) { *out_mask = om; return empty_result(out_buf); }
+    if (n == 0) {
+        if (ec_status s = empty_result(out_buf)) { ec_mask_free(om); return s; }
+        *out_mask = om;
+        return EC_OK;
+    }
     if (t_lazy && lazy_capable(lbuf) && lazy_capable(rbuf)) {  // data deferred (fusable), mask AND now
         if (cudaError_t e = launch_mask_bitop(launch_ctx(), 1, lmask->words, rmask->words, n, om->words)) { ec_mask_free(om); return cuda_fail(e, "mask_bitop"); }
         note_launch("mask_bitop");
@@ -1687,8 +1702,8 @@ ec_status ec_masked_binary(int op, const ec_buf* lbuf, const ec_mask* lmask, con
         *out_mask = om;
         return EC_OK;
     }
-    EC_TRY(resolve(lbuf));
-    EC_TRY(resolve(rbuf));
+    if (ec_status s = resolve(lbuf)) { ec_mask_free(om); return s; }
+    if (ec_status s = resolve(rbuf)) { ec_mask_free(om); return s; }
     ec_buf* o;
     if (ec_status s = new_buf(EC_FLOAT64, n, &o)) { ec_mask_free(om); return s; }
     // The shorter operand's mask has no bits past n, so `&` leaves the last word's tail zero.

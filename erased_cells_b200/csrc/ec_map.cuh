@@ -41,7 +41,8 @@ template <class L, class R> struct NormDiffF {
         const double x = as_f64(a), y = as_f64(b);
         const double num = f64_op<OP_SUB, is_fp<L>, is_fp<R>>(x, y);
         const double den = f64_op<OP_ADD, is_fp<L>, is_fp<R>>(x, y);
-        return f64_op<OP_DIV, true, true>(num, den);
+        // integer bands: num and den are exact (or, for 64-bit cells, rounded) integers within 2^65 -> the guard-free quotient
+        return f64_op<OP_DIV, is_fp<L>, is_fp<R>>(num, den);
     }
 };
 // `(l op1 r) op2 s`

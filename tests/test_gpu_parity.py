@@ -621,3 +621,33 @@ def test_allocation_failure_and_trim():
     ec._lib.check(L.ec_trim())
     assert L.ec_cached_bytes() == 0
     assert CellBuffer.fill(100, CellValue(CellType.Int32, 7)).get(99).value() == 7
+
+
+def test_integer_operand_division_guard_free_sequence(orc):
+    """Division of integer cells runs div.rn.f64's Newton sequence without its range guards (div_int_operands,
+    ec_common.cuh): every quotient, x/0 = +-inf and 0/0 = the x86 default NaN must still match the reference's
+    `(l as f64) / (r as f64)` (src/value.rs:207) bit for bit — plain, fused with a scalar op, and as the quotient
+    of the normalized difference (whose operands are sums / differences of cells, up to 2^65 for 64-bit types)."""
+    n = (1 << 21) + 333
+    rng = np.random.default_rng(0xD1F)
+    for lct, rct in ((CellType.UInt8, CellType.UInt16), (CellType.Int16, CellType.Int16), (CellType.Int32, CellType.UInt8),
+                     (CellType.UInt32, CellType.Int32), (CellType.Int64, CellType.UInt64), (CellType.UInt64, CellType.Int8),
+                     (CellType.Int8, CellType.Int64), (CellType.UInt16, CellType.UInt32)):
+        l, r = synth.host(lct, n, 0x501 + int(lct)).copy(), synth.host(rct, n, 0x601 + int(rct)).copy()
+        # plenty of zeros, ones, extremes and small magnitudes on both sides
+        for a in (l, r):
+            info = np.iinfo(a.dtype)
+            idx = rng.integers(0, n, n // 4)
+            a[idx] = rng.integers(max(info.min, -3), min(info.max, 3) + 1, idx.size).astype(a.dtype)
+            a[rng.integers(0, n, 64)] = info.max
+            a[rng.integers(0, n, 64)] = info.min
+        dl, dr = CellBuffer.from_vec(l), CellBuffer.from_vec(r)
+        want = orc.tight_binary(orc.DIV, l, r)
+        assert np.array_equal(bits((dl / dr).to_vec()), bits(want)), (lct, rct)
+        half = orc.value(orc.Float64, 0.5)
+        assert np.array_equal(bits(dl.binary_scalar(ec.DIV, dr, ec.MUL, 0.5).to_vec()), bits(orc.tight_scalar(orc.MUL, want, half))), (lct, rct)
+        nd = orc.tight_binary(orc.DIV, orc.tight_binary(orc.SUB, l, r), orc.tight_binary(orc.ADD, l, r))
+        assert np.array_equal(bits(dl.normalized_difference(dr).to_vec()), bits(nd)), (lct, rct)
+        with ec.lazy():
+            lz = (dl - dr) / (dl + dr)
+            assert np.array_equal(bits(lz.to_vec()), bits(nd)), (lct, rct)
