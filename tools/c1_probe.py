@@ -71,6 +71,9 @@ for overlap in (1, 0):
             ("python mirror  a / b * 0.5 unfused", timed(lambda i: big[i & 7][0] / big[i & 7][1] * 0.5), 27),
             ("C ABI loop     a / b, 1024 cells (host cost per op)", timed(raw_div(tiny)), 0),
             ("python mirror  a / b, 1024 cells (host cost per op)", timed(lambda i: tiny[i & 7][0] / tiny[i & 7][1]), 0)]
+    rows += [("python mirror  u16 / 10000.0", timed(lambda i: big[i & 7][1] / 10000.0), 10),
+             ("python mirror  u16 / 1e300", timed(lambda i: big[i & 7][1] / 1e300), 10),
+             ("python mirror  u16 * 0.0001", timed(lambda i: big[i & 7][1] * 0.0001), 10)]
     print(f"launch overlap {overlap}, {N} cells, {ITERS} back-to-back ops")
     for name, us, bpc in rows:
         print(f"  {name:56s} {us:8.2f} us" + (f"  {bpc * N / us / 1e3:8.0f} GB/s" if bpc else ""))
