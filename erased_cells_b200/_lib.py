@@ -154,6 +154,7 @@ def _signatures():
         "ec_mask_fill": (S, [SZ, I, PVP]),
         "ec_mask_to_bools": (S, [VP, VP, SZ]),
         "ec_mask_clone": (S, [VP, PVP]),
+        "ec_mask_slice": (S, [VP, SZ, SZ, PVP]),
         "ec_mask_free": (None, [VP]),
         "ec_mask_len": (SZ, [VP]),
         "ec_mask_device_words": (VP, [VP]),

@@ -530,6 +530,12 @@ class Mask:
         check(lib().ec_mask_clone(self._h, C.byref(h)))
         return Mask._take(h)
 
+    def slice(self, offset: int, len_: int) -> "Mask":
+        """Validity bits of cells [offset, offset + len) as a mask of its own (a row strip; offset on a 128-cell boundary)."""
+        h = C.c_void_p()
+        check(lib().ec_mask_slice(self._h, offset, len_, C.byref(h)))
+        return Mask._take(h)
+
     def _op(self, fn, other=None) -> "Mask":
         h = C.c_void_p()
         check(fn(self._h, C.byref(h)) if other is None else fn(self._h, other._h, C.byref(h)))
@@ -670,6 +676,11 @@ class MaskedCellBuffer:
 
     def convert(self, cell_type: CellType) -> "MaskedCellBuffer":
         return MaskedCellBuffer(self._buf.convert(cell_type), self._mask.clone())
+
+    def view(self, offset: int, len_: int) -> "MaskedCellBuffer":
+        """A row strip of a resident masked raster: the buffer half shares the allocation (CellBuffer.view), the mask
+        half is a slice; offset on a 128-cell boundary (ec_row_strip)."""
+        return MaskedCellBuffer(self._buf.view(offset, len_), self._mask.slice(offset, len_))
 
     def min_max(self):
         mn, mx = Value(), Value()

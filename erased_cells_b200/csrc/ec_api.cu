@@ -1532,6 +1532,19 @@ ec_status ec_mask_clone(const ec_mask* m, ec_mask** out) {
     *out = hold.release();
     return EC_OK;
 }
+ec_status ec_mask_slice(const ec_mask* m, size_t offset_cells, size_t len, ec_mask** out) {
+    EC_TRY(ensure());
+    if (offset_cells > m->len || len > m->len - offset_cells) { set_error("slice [%zu, %zu) outside a mask of %zu cells", offset_cells, offset_cells + len, m->len); return EC_OOB; }
+    if (offset_cells % 128 != 0) return invalid("a mask slice must start on a 128-cell boundary (row strips do)");
+    ec_mask* o;
+    EC_TRY(new_mask(len, &o));
+    MaskOwner hold(o, ec_mask_free);
+    // x & x with the strip's words as both operands: the bit-op kernel already clears the bits past `len` in the last word
+    const uint32_t* src = m->words + offset_cells / 32;
+    if (len) EC_LAUNCH(launch_mask_bitop(launch_ctx(), 1, src, src, len, o->words), "mask_slice");
+    *out = hold.release();
+    return EC_OK;
+}
 void ec_mask_free(ec_mask* m) {
     if (!m) return;
     dev_free(m->words);

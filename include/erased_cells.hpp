@@ -198,6 +198,8 @@ public:
     size_t len() const { return ec_buf_len(h_); }
     bool is_empty() const { return len() == 0; }
     CellType cell_type() const { return CellType(ec_buf_ctype(h_)); }
+    // cells [offset, offset + len) as a buffer sharing this allocation (a row strip; offset on a 32-byte boundary)
+    CellBuffer view(size_t offset, size_t len) const { ec_buf* h; detail::check(ec_buf_view(h_, offset, len, &h)); return own(h); }
     CellValue get(size_t index) const { CellValue o; detail::check(ec_buf_get(h_, index, &o.v)); return o; }
     void put(size_t index, const CellValue& value) { detail::check(ec_buf_put(h_, index, &value.v)); }
     template <class T> void extend(const std::vector<T>& more) { detail::check(ec_buf_extend_host(h_, uint8_t(CellEncoding<T>::cell_type()), more.data(), more.size())); }
@@ -294,6 +296,8 @@ public:
         detail::check(ec_mask_to_bools(h_, b.data(), b.size()));
         return std::vector<bool>(b.begin(), b.end());
     }
+    // validity bits of cells [offset, offset + len) as a mask of its own (a row strip; offset on a 128-cell boundary)
+    Mask slice(size_t offset, size_t len) const { ec_mask* h; detail::check(ec_mask_slice(h_, offset, len, &h)); return own(h); }
     Mask operator!() const { ec_mask* h; detail::check(ec_mask_not(h_, &h)); return own(h); }
     Mask operator&(const Mask& o) const { ec_mask* h; detail::check(ec_mask_and(h_, o.h_, &h)); return own(h); }
     Mask operator|(const Mask& o) const { ec_mask* h; detail::check(ec_mask_or(h_, o.h_, &h)); return own(h); }
@@ -352,6 +356,8 @@ public:
         for (size_t i = 0; i < len; ++i) { auto p = mv(i); d[i] = p.first; m[i] = p.second; }
         return MaskedCellBuffer(CellBuffer::from_vec(d), Mask(m));
     }
+    // a row strip of a resident masked raster (offset on a 128-cell boundary, ec_row_strip)
+    MaskedCellBuffer view(size_t offset, size_t len) const { return MaskedCellBuffer(buf_.view(offset, len), mask_.slice(offset, len)); }
     const CellBuffer& buffer() const { return buf_; }
     CellBuffer& buffer_mut() { return buf_; }
     const Mask& mask() const { return mask_; }

@@ -248,6 +248,11 @@ ec_status ec_mask_from_bools(const uint8_t* host_bools, size_t len, ec_mask** ou
 ec_status ec_mask_fill(size_t len, int value, ec_mask** out);                        /* :21-23 */
 ec_status ec_mask_to_bools(const ec_mask* m, uint8_t* host_bools, size_t capacity);  /* IntoIterator :171-177 */
 ec_status ec_mask_clone(const ec_mask* m, ec_mask** out);
+/* the validity bits of a row strip (cells [offset, offset + len) of the mask, offset a multiple of 128 cells like every
+ * strip start) as a mask of its own — the Mask half of a MaskedCellBuffer strip whose buffer half is ec_buf_view. A copy
+ * (1/8 byte per cell): a packed mask keeps the bits past its length zero, which a window into another mask's words
+ * could not guarantee. */
+ec_status ec_mask_slice(const ec_mask* m, size_t offset_cells, size_t len, ec_mask** out);
 void ec_mask_free(ec_mask* m);
 size_t ec_mask_len(const ec_mask* m);                                               /* :37-39 */
 void* ec_mask_device_words(const ec_mask* m);

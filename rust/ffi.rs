@@ -67,6 +67,7 @@ extern "C" {
     pub fn ec_mask_fill(len: usize, value: c_int, out: *mut *mut ec_mask) -> ec_status;
     pub fn ec_mask_to_bools(m: *const ec_mask, bools: *mut u8, capacity: usize) -> ec_status;
     pub fn ec_mask_clone(m: *const ec_mask, out: *mut *mut ec_mask) -> ec_status;
+    pub fn ec_mask_slice(m: *const ec_mask, offset_cells: usize, len: usize, out: *mut *mut ec_mask) -> ec_status;
     pub fn ec_mask_free(m: *mut ec_mask);
     pub fn ec_mask_len(m: *const ec_mask) -> usize;
     pub fn ec_mask_get(m: *const ec_mask, index: usize, out: *mut c_int) -> ec_status;

@@ -609,6 +609,36 @@ def test_views_share_the_allocation(orc):
         strips[0].view(3, 10)
 
 
+def test_masked_row_strips_of_a_resident_raster(orc):
+    """MaskedCellBuffer.view = ec_buf_view + ec_mask_slice: strips of a resident masked raster behave like masked
+    buffers built from the same cells (mask bits, counts, masked min_max, ops), including a ragged last strip whose
+    length is not a multiple of 32 (the slice keeps the bits past its length zero)."""
+    n = 3 * 4096 + 1000 + 13
+    h = synth.host(CellType.Int16, n, 0x51F, kind=synth.INT_RANGE, lo=-50, hi=50)
+    whole = MaskedCellBuffer.from_vec_with_nodata(h, NoData.new(CellType.Int16, 7))
+    hm = h != 7
+    bounds = [(0, 4096), (4096, 4096), (8192, 4096), (12288, n - 12288), (12288 + 128, 77), (4096, 0)]
+    for off, ln in bounds:
+        s = whole.view(off, ln)
+        assert s.len() == ln and s.mask().len() == ln
+        assert np.array_equal(s.mask().to_vec(), hm[off:off + ln])
+        assert s.counts() == orc.mask_counts(hm[off:off + ln])
+        if ln:
+            mn, mx = s.min_max()
+            omn, omx = orc.tight_min_max(h[off:off + ln], hm[off:off + ln])
+            assert (mn.bits, mx.bits) == (omn.bits, omx.bits)
+            assert (~s.mask()).counts() == orc.mask_counts(~hm[off:off + ln])   # tail bits of the slice are zero
+    a, b = whole.view(0, 4096), whole.view(4096, 4096)
+    d = a - b
+    assert np.array_equal(bits(d.buffer().to_vec()), bits(orc.tight_binary(orc.SUB, h[:4096], h[4096:8192])))
+    assert np.array_equal(d.mask().to_vec(), hm[:4096] & hm[4096:8192])
+    assert whole.mask().slice(0, n) == whole.mask()
+    with pytest.raises(IndexError):
+        whole.mask().slice(128, n)
+    with pytest.raises(ec.EcError):
+        whole.mask().slice(32, 64)
+
+
 def test_allocation_failure_and_trim():
     """An impossible allocation is an error code (MemoryError here), not a crash; the block cache can be handed back."""
     L = ec.lib()
