@@ -18,7 +18,8 @@ template <int A, int B> __host__ __device__ constexpr int cmax() { return A > B 
 template <class L, class R, int OP> struct BinaryF {  // src/value.rs:199-209
     using A = L; using B = R; using O = double;
     __device__ __forceinline__ double operator()(L a, R b) const {
-        return f64_op<OP, is_fp<L>, is_fp<R>>(as_f64(a), as_f64(b));
+        if constexpr (OP == OP_DIV) return f64_div_cells<L, R>(as_f64(a), as_f64(b));
+        else return f64_op<OP, is_fp<L>, is_fp<R>>(as_f64(a), as_f64(b));
     }
 };
 template <class L> struct ScalarF {  // src/buffer.rs:346-352; rhs is `s as f64`, converted once on the host
@@ -42,7 +43,7 @@ template <class L, class R> struct NormDiffF {
         const double num = f64_op<OP_SUB, is_fp<L>, is_fp<R>>(x, y);
         const double den = f64_op<OP_ADD, is_fp<L>, is_fp<R>>(x, y);
         // integer bands: num and den are exact (or, for 64-bit cells, rounded) integers within 2^65 -> the guard-free quotient
-        return f64_op<OP_DIV, is_fp<L>, is_fp<R>>(num, den);
+        return f64_div_cells<L, R>(num, den);
     }
 };
 // `(l op1 r) op2 s`
@@ -61,7 +62,9 @@ template <class L, class R, int OP1, int OP2> struct BinaryScalarT {
     using A = L; using B = R; using O = double;
     double s;
     __device__ __forceinline__ double operator()(L a, R b) const {
-        const double t = f64_op<OP1, is_fp<L>, is_fp<R>>(as_f64(a), as_f64(b));
+        double t;
+        if constexpr (OP1 == OP_DIV) t = f64_div_cells<L, R>(as_f64(a), as_f64(b));
+        else t = f64_op<OP1, is_fp<L>, is_fp<R>>(as_f64(a), as_f64(b));
         return f64_op<OP2, true, true>(t, s);
     }
 };

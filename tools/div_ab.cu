@@ -27,6 +27,16 @@ template <class L, class R> struct DivGeneric {
     }
 };
 
+template <class L, class R> struct DivGenericFp {
+    using A = L; using B = R; using O = double;
+    __device__ __forceinline__ double operator()(L a, R b) const {
+        const double x = as_f64(a), y = as_f64(b);
+        double r = __ddiv_rn(x, y);
+        if (r != r) r = x86_nan_result(x, y);
+        return r;
+    }
+};
+
 template <class F> static float run(const typename F::A* a, const typename F::B* b, double* o, size_t n, int iters, cudaEvent_t e0, cudaEvent_t e1) {
     constexpr int V = 32 / 8;
     constexpr size_t TILE = size_t(256) * V * 4;
@@ -44,6 +54,12 @@ __global__ void fill16(uint16_t* p, size_t n, uint64_t seed, uint32_t lo, uint32
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
         p[i] = uint16_t(lo + splitmix64(seed ^ i) % span);
 }
+__global__ void fillf(float* p, size_t n, uint64_t seed) {  // reflectance-like: (0, 1], a few exact zeros
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        const uint64_t h = splitmix64(seed ^ i);
+        p[i] = (h % 1000 == 0) ? 0.0f : float((h >> 11) * 0x1p-53);
+    }
+}
 __global__ void fill8(uint8_t* p, size_t n, uint64_t seed) {
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) p[i] = uint8_t(splitmix64(seed ^ i));
 }
@@ -54,6 +70,7 @@ int main() {
     CK(cudaMalloc(&a, N * 2)); CK(cudaMalloc(&b, N * 2)); CK(cudaMalloc(&c, N)); CK(cudaMalloc(&o, N * 8));
     fill16<<<4096, 256>>>(a, N, 1, 5000, 35001); fill16<<<4096, 256>>>(b, N, 2, 5000, 35001); fill8<<<4096, 256>>>(c, N, 3);
     CK(cudaDeviceSynchronize());
+    float *fa = reinterpret_cast<float*>(a), *fb = reinterpret_cast<float*>(b);  // the same arenas, 2^29 f32 cells each
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (size_t n : {size_t(1) << 24, size_t(1) << 26, size_t(1) << 28, size_t(1) << 30}) {
         const int iters = n >= (size_t(1) << 28) ? 5 : 40;
@@ -67,6 +84,21 @@ int main() {
         }
         printf("n=2^%d  normdiff_u16: guard-free %.4f ms (%.0f GB/s)  generic %.4f ms (%.0f GB/s)   div_u8_u16: guard-free %.4f ms (%.0f GB/s)  generic %.4f ms (%.0f GB/s)\n",
                63 - __builtin_clzll(n), t[0], 12.0 * n / t[0] / 1e6, t[1], 12.0 * n / t[1] / 1e6, t[2], 11.0 * n / t[2] / 1e6, t[3], 11.0 * n / t[3] / 1e6);
+    }
+    fillf<<<4096, 256>>>(fa, N / 2, 4); fillf<<<4096, 256>>>(fb, N / 2, 5);
+    CK(cudaDeviceSynchronize());
+    for (size_t n : {size_t(1) << 24, size_t(1) << 26, size_t(1) << 28, size_t(1) << 29}) {
+        const int iters = n >= (size_t(1) << 28) ? 5 : 40;
+        float t[4] = {0, 0, 0, 0};
+        for (int rep = 0; rep < 4; ++rep) {
+            const float x0 = run<NormDiffF<float, float>>(fa, fb, o, n, iters, e0, e1);
+            const float x1 = run<NormDiffGeneric<float, float>>(fa, fb, o, n, iters, e0, e1);
+            const float x2 = run<BinaryF<float, float, OP_DIV>>(fa, fb, o, n, iters, e0, e1);
+            const float x3 = run<DivGenericFp<float, float>>(fa, fb, o, n, iters, e0, e1);
+            if (rep) { t[0] += x0 / 3; t[1] += x1 / 3; t[2] += x2 / 3; t[3] += x3 / 3; }
+        }
+        printf("n=2^%d  normdiff_f32: guard-free %.4f ms (%.0f GB/s)  generic %.4f ms (%.0f GB/s)   div_f32_f32: guard-free %.4f ms (%.0f GB/s)  generic %.4f ms (%.0f GB/s)\n",
+               63 - __builtin_clzll(n), t[0], 16.0 * n / t[0] / 1e6, t[1], 16.0 * n / t[1] / 1e6, t[2], 16.0 * n / t[2] / 1e6, t[3], 16.0 * n / t[3] / 1e6);
     }
     return 0;
 }
