@@ -341,7 +341,9 @@ def run_ours(args, out):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic, "peak_source": peak_src, "frac_of_nominal_8TBs": round(achieved / NOMINAL_GBS, 4),
+                "traffic": (traffic // len(pairs)) if traffic else None, "traffic_per_step": traffic,
+                "traffic_source": "profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of the step's 41 launches under ncu, per launch = / 41",
+                "peak_source": peak_src, "frac_of_nominal_8TBs": round(achieved / NOMINAL_GBS, 4),
                 "kernel": "map1_kernel<CastF<S,D>> family: 31 casts + 10 clones per step (100% of the step's kernels)",
                 "algorithmic_bytes_per_step": step_bytes, "launches_per_step": len(pairs),
                 "avg_launch_ms": round(ms_per_step / len(pairs), 5), "algorithmic_bytes_per_launch": step_bytes // len(pairs),
