@@ -83,6 +83,13 @@ impl CellBuffer {
     pub fn new<T: CellEncoding>(data: Vec<T>) -> Self {
         Self::from_vec(data)
     }
+    /// Extension: cells `[offset, offset + len)` as a buffer sharing this allocation (a row strip of a resident
+    /// raster; `offset` on a 32-byte boundary). No copy; a later `put` / `extend` through either handle copies first.
+    pub fn view(&self, offset: usize, len: usize) -> Self {
+        let mut h = ptr::null_mut();
+        check(unsafe { ec_buf_view(self.0, offset, len, &mut h) }).unwrap();
+        Self(h)
+    }
 }
 
 impl BufferOps for CellBuffer {
@@ -258,6 +265,12 @@ impl Mask {
     pub fn fill_via<F: Fn(usize) -> bool>(len: usize, f: F) -> Self {
         Self::new((0..len).map(f).collect())
     }
+    /// Extension: the validity bits of cells `[offset, offset + len)` as a mask of its own (`offset` a multiple of 128).
+    pub fn slice(&self, offset: usize, len: usize) -> Self {
+        let mut h = ptr::null_mut();
+        check(unsafe { ec_mask_slice(self.0, offset, len, &mut h) }).unwrap();
+        Self(h)
+    }
     pub fn len(&self) -> usize {
         unsafe { ec_mask_len(self.0) }
     }
@@ -346,6 +359,10 @@ impl MaskedCellBuffer {
         let mut m = ptr::null_mut();
         check(unsafe { ec_mask_from_nodata(buf.0, kind, &v, &mut m) }).unwrap();
         Self(buf, Mask(m))
+    }
+    /// Extension: a row strip of a resident masked raster (`offset` a multiple of 128 cells, see `ec_row_strip`).
+    pub fn view(&self, offset: usize, len: usize) -> Self {
+        Self(self.0.view(offset, len), self.1.slice(offset, len))
     }
     pub fn buffer(&self) -> &CellBuffer {
         &self.0

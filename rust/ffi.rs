@@ -53,6 +53,7 @@ extern "C" {
     pub fn ec_buf_extend_host(b: *mut ec_buf, ct: u8, host: *const c_void, n: usize) -> ec_status;
     pub fn ec_buf_from_host_async(ct: u8, host: *const c_void, len: usize, out: *mut *mut ec_buf) -> ec_status;
     pub fn ec_buf_wait(b: *const ec_buf) -> ec_status;
+    pub fn ec_buf_view(b: *const ec_buf, offset_cells: usize, len: usize, out: *mut *mut ec_buf) -> ec_status;
     pub fn ec_set_lazy(mode: c_int) -> ec_status;
     pub fn ec_set_launch_overlap(on: c_int) -> c_int;
     pub fn ec_buf_binary(op: c_int, l: *const ec_buf, r: *const ec_buf, out: *mut *mut ec_buf) -> ec_status;
