@@ -710,3 +710,42 @@ def test_integer_cells_divided_by_scalars_of_every_magnitude(orc):
         assert np.array_equal(bits((d / sv).to_vec()), bits(want)), sv
     hf = cells(CellType.Float32, n, 0x7F1)
     assert np.array_equal(bits((CellBuffer.from_vec(hf) / 10000.0).to_vec()), bits(orc.tight_scalar(orc.DIV, hf, orc.value(orc.Float64, 10000.0))))
+
+
+def _special_cells(ct):
+    dt = CellType(ct).dtype
+    if dt == np.float32:
+        raw = np.array([0x00000000, 0x80000000, 0x7F800000, 0xFF800000, 0x7FC00000, 0xFFC00000, 0x7F800001, 0xFFBFFFFF, 0x3F800000, 0xBF800000,
+                        0x00000001, 0x80000001, 0x7F7FFFFF, 0x3FC00000, 0x80800000, 0x4B800000], np.uint32)
+        return raw.view(np.float32)
+    if dt == np.float64:
+        raw = np.array([0, 1 << 63, 0x7FF << 52, 0xFFF << 52, 0x7FF8 << 48, 0xFFF8 << 48, (0x7FF << 52) | 1, (0xFFF << 52) | 0x7FFFFFFFFFFFF, 0x3FF << 52,
+                        0xBFF << 52, 1, (1 << 63) | 1, 0x7FEFFFFFFFFFFFFF, 0x3FF8 << 48, 0x0010000000000000, 0x4330000000000000], np.uint64)
+        return raw.view(np.float64)
+    info = np.iinfo(dt)
+    return np.array([0, 1, info.max, info.min, 7, info.max // 3] + ([-1, -7] if info.min < 0 else [2, 255]), dt)
+
+
+def test_special_value_cross_product_all_ops_and_fused(orc):
+    """Every pairing of zeros, infinities, quiet / signalling NaNs of both signs, subnormals and extremes, as a vectorised
+    body and as a ragged tail: the four ops, the fused `(l op r) op s` and the normalized difference must match the
+    reference's f64 arithmetic on its platform (src/value.rs:207; NaN results by the x86 rule) bit for bit. Covers the
+    division variants by operand origin (integer / integer, f32 or integer on both sides, any f64)."""
+    pairs = [(CellType.Float32, CellType.Float32), (CellType.Float32, CellType.Int16), (CellType.UInt8, CellType.Float32),
+             (CellType.Float32, CellType.UInt64), (CellType.Int64, CellType.Float32), (CellType.Float32, CellType.Float64),
+             (CellType.Float64, CellType.Float32), (CellType.Float64, CellType.Float64), (CellType.Int32, CellType.Int8),
+             (CellType.Float64, CellType.UInt16)]
+    for lct, rct in pairs:
+        sl, sr = _special_cells(lct), _special_cells(rct)
+        l0, r0 = np.repeat(sl, len(sr)), np.tile(sr, len(sl))
+        reps = (3 * 16384 + 77) // len(l0) + 1
+        l, r = np.tile(l0, reps)[: 3 * 16384 + 77].copy(), np.tile(r0, reps)[: 3 * 16384 + 77].copy()
+        dl, dr = CellBuffer.from_vec(l), CellBuffer.from_vec(r)
+        for op in range(4):
+            want = orc.tight_binary(op, l, r)
+            assert np.array_equal(bits(dl._bin(op, dr).to_vec()), bits(want)), (lct, rct, op)
+            for op2, s in ((orc.MUL, 0.5), (orc.ADD, np.inf), (orc.DIV, 0.0)):
+                got = dl.binary_scalar(op, dr, op2, s).to_vec()
+                assert np.array_equal(bits(got), bits(orc.tight_scalar(op2, want, orc.value(orc.Float64, s)))), (lct, rct, op, op2, s)
+        nd = orc.tight_binary(orc.DIV, orc.tight_binary(orc.SUB, l, r), orc.tight_binary(orc.ADD, l, r))
+        assert np.array_equal(bits(dl.normalized_difference(dr).to_vec()), bits(nd)), (lct, rct)
