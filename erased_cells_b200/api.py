@@ -621,6 +621,24 @@ class MaskedCellBuffer:
         return MaskedCellBuffer.from_buffer_with_nodata(b, nodata)
 
     @staticmethod
+    def from_iter(items, ct: CellType | None = None) -> "MaskedCellBuffer":
+        """FromIterator<C> (src/masked/masked_buffer.rs:257-261: all cells valid) and FromIterator<(C, bool)> (:263-278):
+        plain cells, or (cell, valid) pairs. The cell type is `ct`, else numpy scalars keep theirs and Python numbers
+        follow Rust's literal defaults (int -> i32, float -> f64); an empty iterator of pairs gives `ct` (default Int32) cells."""
+        items = list(items)
+        paired = bool(items) and isinstance(items[0], tuple)
+        cells = [p[0] for p in items] if paired else items
+        if ct is not None:
+            dt = _DTYPES[int(ct)]
+        elif cells:
+            v0 = cells[0]
+            dt = v0.dtype if isinstance(v0, np.generic) else (np.int32 if isinstance(v0, int) else np.float64)
+        else:
+            dt = np.int32
+        buf = CellBuffer.from_vec(np.array(cells, dtype=dt)) if cells else CellBuffer.with_defaults(0, CellType.of(np.dtype(dt)))
+        return MaskedCellBuffer(buf, Mask.new([bool(p[1]) for p in items]) if paired else Mask.fill(len(cells), True))
+
+    @staticmethod
     def from_buffer_with_nodata(b: CellBuffer, nodata: NoData) -> "MaskedCellBuffer":
         h = C.c_void_p()
         check(lib().ec_mask_from_nodata(b._h, nodata.kind, nodata._ptr(), C.byref(h)))

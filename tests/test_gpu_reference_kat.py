@@ -190,6 +190,11 @@ def test_masked_extend_and_from_iter():  # src/masked/masked_buffer.rs:449-462
     assert buf.get_masked(0) == CellValue.new(0) and buf.get_masked(3) is None
     buf = MaskedCellBuffer.from_vec(np.arange(5, dtype=np.int16))
     assert buf.mask().all(True) and list(buf.to_vec(CellType.Int16)) == [0, 1, 2, 3, 4]
+    buf = MaskedCellBuffer.from_iter(np.arange(5, dtype=np.int16))            # `(0..5i16).collect()`, :458-462
+    assert buf.cell_type() == CellType.Int16 and buf.mask().all(True) and list(buf.to_vec(CellType.Int16)) == [0, 1, 2, 3, 4]
+    buf = MaskedCellBuffer.from_iter((np.uint8(i), i % 2 == 0) for i in range(5))  # FromIterator<(C, bool)>, :263-278
+    assert buf.cell_type() == CellType.UInt8 and buf.counts() == (3, 2) and buf.get_masked(1) is None and buf.get_masked(4) == CellValue.new(np.uint8(4))
+    assert MaskedCellBuffer.from_iter([], CellType.Float32).cell_type() == CellType.Float32
 
 
 def test_masked_convert():  # src/masked/masked_buffer.rs:442-447
