@@ -174,3 +174,42 @@ def test_fill_nodata_and_truncation(orc):
         orc.fill_nodata(a.astype(np.float64), m, orc.Int32, orc.ND_DEFAULT)
     # length mismatch truncates to the shorter operand (zip) — src/buffer.rs:327
     assert len(orc.binary(orc.ADD, np.ones(5, np.uint8), np.ones(3, np.float32))) == 3
+
+
+def test_special_value_cross_product_against_an_independent_statement(orc):
+    """Every pairing of zeros, infinities, NaNs of both signs and kinds, subnormals and extremes through the four ops:
+    the oracle's non-NaN results equal numpy's IEEE arithmetic bit for bit, and its NaN results follow the x86 rule
+    stated here independently (first NaN operand, quieted; else the negative default NaN). This is the table the GPU
+    test of the same name checks the kernels against."""
+    raw64 = np.array([0, 1 << 63, 0x7FF << 52, 0xFFF << 52, 0x7FF8 << 48, 0xFFF8 << 48, (0x7FF << 52) | 1, (0xFFF << 52) | 0x7FFFFFFFFFFFF,
+                      0x3FF << 52, 0xBFF << 52, 1, (1 << 63) | 1, 0x7FEFFFFFFFFFFFFF, 0x3FF8 << 48, 0x0010000000000000, 0x4330000000000000], np.uint64)
+    raw32 = np.array([0x00000000, 0x80000000, 0x7F800000, 0xFF800000, 0x7FC00000, 0xFFC00000, 0x7F800001, 0xFFBFFFFF, 0x3F800000, 0xBF800000,
+                      0x00000001, 0x80000001, 0x7F7FFFFF, 0x3FC00000, 0x80800000, 0x4B800000], np.uint32)
+
+    def widen32(u):  # cvtss2sd on NaNs: sign and payload kept, quiet bit set
+        f = u.view(np.float32)
+        with np.errstate(all="ignore"):
+            d = f.astype(np.float64).view(np.uint64).copy()
+        nan = np.isnan(f)
+        d[nan] = ((u[nan].astype(np.uint64) & 0x80000000) << 32) | 0x7FF8000000000000 | ((u[nan].astype(np.uint64) & 0x007FFFFF) << 29)
+        return d
+
+    for lraw, rraw in ((raw64, raw64), (raw32, raw32), (raw32, raw64), (raw64, raw32)):
+        l0, r0 = np.repeat(lraw, len(rraw)), np.tile(rraw, len(lraw))
+        lcells = l0.view(np.float32 if l0.dtype == np.uint32 else np.float64)
+        rcells = r0.view(np.float32 if r0.dtype == np.uint32 else np.float64)
+        lb = widen32(l0) if l0.dtype == np.uint32 else l0.copy()
+        rb = widen32(r0) if r0.dtype == np.uint32 else r0.copy()
+        ld, rd = lb.view(np.float64), rb.view(np.float64)
+        for op, fn in ((orc.ADD, np.add), (orc.SUB, np.subtract), (orc.MUL, np.multiply), (orc.DIV, np.divide)):
+            with np.errstate(all="ignore"):
+                plain = fn(ld, rd)
+            want = plain.view(np.uint64).copy()
+            isn = np.isnan(plain)
+            want[isn] = 0xFFF8000000000000
+            rn, ln = np.isnan(rd), np.isnan(ld)
+            want[rn] = rb[rn] | 0x0008000000000000
+            want[ln] = lb[ln] | 0x0008000000000000
+            got = bits(orc.tight_binary(op, lcells, rcells))
+            assert np.array_equal(got, want), (lraw.dtype, rraw.dtype, op, np.flatnonzero(got != want)[:5])
+            assert np.array_equal(bits(orc.binary(op, lcells, rcells)), want)
