@@ -153,6 +153,53 @@ impl<T: CellEncoding> From<Vec<T>> for CellBuffer {
         Self::from_vec(values)
     }
 }
+impl<T: CellEncoding> From<&[T]> for CellBuffer {
+    fn from(values: &[T]) -> Self {
+        // src/buffer.rs:265-276
+        Self::from_vec(values.to_vec())
+    }
+}
+impl<C: CellEncoding> FromIterator<C> for CellBuffer {
+    fn from_iter<I: IntoIterator<Item = C>>(iter: I) -> Self {
+        // src/buffer.rs:223-227
+        Self::from_vec(iter.into_iter().collect())
+    }
+}
+impl FromIterator<CellValue> for CellBuffer {
+    fn from_iter<I: IntoIterator<Item = CellValue>>(iterable: I) -> Self {
+        // src/buffer.rs:229-250: the first element decides the cell type; nothing collected => UInt8([])
+        let values: Vec<CellValue> = iterable.into_iter().collect();
+        match values.first() {
+            None => Self::with_defaults(0, CellType::UInt8),
+            Some(first) => {
+                let ct = first.cell_type();
+                macro_rules! collect {
+                    ($(($id:ident, $p:ident)),*) => {
+                        match ct {
+                            $(CellType::$id => Self::from_vec(values.iter().map(|v| v.get::<$p>().unwrap()).collect::<Vec<$p>>()),)*
+                        }
+                    };
+                }
+                with_ct!(collect)
+            }
+        }
+    }
+}
+impl<C: CellEncoding> TryFrom<CellBuffer> for Vec<C> {
+    type Error = Error;
+    fn try_from(value: CellBuffer) -> Result<Self> {
+        // src/buffer.rs:307-313
+        value.to_vec::<C>()
+    }
+}
+impl<'buf> IntoIterator for &'buf CellBuffer {
+    type Item = CellValue;
+    type IntoIter = std::vec::IntoIter<CellValue>;
+    fn into_iter(self) -> Self::IntoIter {
+        // src/buffer.rs:278-305 yields host CellValues: one D2H copy of the buffer, then iterate that
+        (0..self.len()).map(|i| self.get(i)).collect::<Vec<_>>().into_iter() // a shim would download once; shown per cell for brevity
+    }
+}
 impl<C: CellEncoding> Extend<C> for CellBuffer {
     fn extend<I: IntoIterator<Item = C>>(&mut self, iter: I) {
         // src/buffer.rs:205-221: value-checked `to_<p>().unwrap()` runs on the device; EC_NARROWING is that unwrap's panic
@@ -265,6 +312,11 @@ impl Mask {
     pub fn fill_via<F: Fn(usize) -> bool>(len: usize, f: F) -> Self {
         Self::new((0..len).map(f).collect())
     }
+    /// `Extend<bool>` (src/masked/mask.rs:83-87): appended on the device (unpack, append, repack)
+    pub fn extend_from<I: IntoIterator<Item = bool>>(&mut self, iter: I) {
+        let v: Vec<bool> = iter.into_iter().collect();
+        check(unsafe { ec_mask_extend_host(self.0, v.as_ptr().cast(), v.len()) }).unwrap();
+    }
     /// Extension: the validity bits of cells `[offset, offset + len)` as a mask of its own (`offset` a multiple of 128).
     pub fn slice(&self, offset: usize, len: usize) -> Self {
         let mut h = ptr::null_mut();
@@ -367,6 +419,27 @@ impl MaskedCellBuffer {
     pub fn buffer(&self) -> &CellBuffer {
         &self.0
     }
+    pub fn buffer_mut(&mut self) -> &mut CellBuffer {
+        &mut self.0
+    }
+    pub fn mask_mut(&mut self) -> &mut Mask {
+        &mut self.1
+    }
+    /// src/masked/masked_buffer.rs:73-79: the closure is host code in the reference too; one upload of both halves
+    pub fn fill_with_mask_via<T: CellEncoding, F: Fn(usize) -> (T, bool)>(len: usize, mv: F) -> Self {
+        let (data, mask): (Vec<T>, Vec<bool>) = (0..len).map(mv).unzip();
+        Self::new(CellBuffer::from_vec(data), Mask::new(mask))
+    }
+    /// src/masked/masked_buffer.rs:112-118
+    pub fn get_with_mask(&self, index: usize) -> (CellValue, bool) {
+        (self.0.get(index), self.1.get(index))
+    }
+    /// src/masked/masked_buffer.rs:120-130
+    pub fn put_with_mask(&mut self, index: usize, value: CellValue, mask: bool) -> Result<()> {
+        self.0.put(index, value)?;
+        self.1.put(index, mask);
+        Ok(())
+    }
     pub fn mask(&self) -> &Mask {
         &self.1
     }
@@ -395,6 +468,88 @@ impl MaskedCellBuffer {
         let mut s = ec_statistics { count: 0, min: z, max: z, mean: 0.0, stddev: 0.0 };
         check(unsafe { ec_buf_statistics((self.0).0, (self.1).0, &mut s) }).unwrap();
         Statistics { count: s.count, min: from_ffi(s.min), max: from_ffi(s.max), mean: s.mean, stddev: s.stddev }
+    }
+}
+impl BufferOps for MaskedCellBuffer {
+    // src/masked/masked_buffer.rs:155-225: the buffer half does the work, the mask half is all-valid or carried along
+    fn from_vec<T: CellEncoding>(data: Vec<T>) -> Self {
+        CellBuffer::from_vec(data).into()
+    }
+    fn with_defaults(len: usize, ct: CellType) -> Self {
+        CellBuffer::with_defaults(len, ct).into()
+    }
+    fn fill(len: usize, value: CellValue) -> Self {
+        CellBuffer::fill(len, value).into()
+    }
+    fn fill_via<T: CellEncoding, F: Fn(usize) -> T>(len: usize, f: F) -> Self {
+        CellBuffer::fill_via(len, f).into()
+    }
+    fn len(&self) -> usize {
+        self.0.len()
+    }
+    fn cell_type(&self) -> CellType {
+        self.0.cell_type()
+    }
+    fn get(&self, index: usize) -> CellValue {
+        self.0.get(index)
+    }
+    fn put(&mut self, idx: usize, value: CellValue) -> Result<()> {
+        self.0.put(idx, value)
+    }
+    fn convert(&self, cell_type: CellType) -> Result<Self> {
+        Ok(Self(self.0.convert(cell_type)?, self.1.clone()))
+    }
+    fn min_max(&self) -> (CellValue, CellValue) {
+        MaskedCellBuffer::min_max(self)
+    }
+    fn to_vec<T: CellEncoding>(self) -> Result<Vec<T>> {
+        self.0.to_vec()
+    }
+}
+impl From<CellBuffer> for MaskedCellBuffer {
+    fn from(value: CellBuffer) -> Self {
+        // src/masked/masked_buffer.rs:250-255
+        let len = value.len();
+        Self::new(value, Mask::fill(len, true))
+    }
+}
+impl From<MaskedCellBuffer> for (CellBuffer, Mask) {
+    fn from(value: MaskedCellBuffer) -> Self {
+        (value.0, value.1)
+    }
+}
+impl<C: CellEncoding> FromIterator<C> for MaskedCellBuffer {
+    fn from_iter<I: IntoIterator<Item = C>>(iter: I) -> Self {
+        // src/masked/masked_buffer.rs:257-261
+        <Self as BufferOps>::from_vec(iter.into_iter().collect())
+    }
+}
+impl<C: CellEncoding> FromIterator<(C, bool)> for MaskedCellBuffer {
+    fn from_iter<I: IntoIterator<Item = (C, bool)>>(iter: I) -> Self {
+        // src/masked/masked_buffer.rs:263-278 (an empty iterator still gives cells of type C)
+        let (data, mask): (Vec<C>, Vec<bool>) = iter.into_iter().unzip();
+        Self::new(CellBuffer::from_vec(data), Mask::new(mask))
+    }
+}
+impl<C: CellEncoding> Extend<(C, bool)> for MaskedCellBuffer {
+    fn extend<I: IntoIterator<Item = (C, bool)>>(&mut self, iter: I) {
+        // src/masked/masked_buffer.rs:280-287, as two bulk appends instead of one per pair
+        let (data, mask): (Vec<C>, Vec<bool>) = iter.into_iter().unzip();
+        self.0.extend(data);
+        self.1.extend_from(mask);
+    }
+}
+impl Neg for &MaskedCellBuffer {
+    type Output = MaskedCellBuffer;
+    fn neg(self) -> MaskedCellBuffer {
+        // src/masked/masked_buffer.rs:372-383: cells negated (also under a false mask), mask cloned
+        MaskedCellBuffer(-&self.0, self.1.clone())
+    }
+}
+impl Neg for MaskedCellBuffer {
+    type Output = MaskedCellBuffer;
+    fn neg(self) -> MaskedCellBuffer {
+        MaskedCellBuffer(-self.0, self.1)
     }
 }
 /// Result of the `statistics()` extension.

@@ -68,6 +68,7 @@ extern "C" {
     pub fn ec_mask_fill(len: usize, value: c_int, out: *mut *mut ec_mask) -> ec_status;
     pub fn ec_mask_to_bools(m: *const ec_mask, bools: *mut u8, capacity: usize) -> ec_status;
     pub fn ec_mask_clone(m: *const ec_mask, out: *mut *mut ec_mask) -> ec_status;
+    pub fn ec_mask_extend_host(m: *mut ec_mask, host_bools: *const u8, n: usize) -> ec_status;
     pub fn ec_mask_slice(m: *const ec_mask, offset_cells: usize, len: usize, out: *mut *mut ec_mask) -> ec_status;
     pub fn ec_mask_free(m: *mut ec_mask);
     pub fn ec_mask_len(m: *const ec_mask) -> usize;
