@@ -31,6 +31,12 @@ class Statistics(C.Structure):
 MOMENT_WORDS = 9
 
 
+class ShardInfo(C.Structure):
+    """ec_shard_info: where one row strip of a sharded buffer / mask lives."""
+    _fields_ = [("logical_device", C.c_int), ("cuda_device", C.c_int), ("offset", C.c_size_t), ("len", C.c_size_t),
+                ("device_ptr", C.c_void_p)]
+
+
 class DeviceInfo(C.Structure):
     _fields_ = [("device", C.c_int), ("sm_count", C.c_int), ("cc_major", C.c_int), ("cc_minor", C.c_int),
                 ("l2_bytes", C.c_size_t), ("total_mem_bytes", C.c_size_t), ("name", C.c_char * 128)]
@@ -80,6 +86,14 @@ def _signatures():
         "ec_last_error": (C.c_char_p, []),
         "ec_last_narrowing": (None, [C.POINTER(U8), C.POINTER(U8)]),
         "ec_init": (S, [I]),
+        "ec_init_devices": (S, [PI, I]),
+        "ec_device_count": (I, []),
+        "ec_set_shard_min_cells": (SZ, [SZ]),
+        "ec_set_shard_finish": (I, [I]),
+        "ec_buf_shard_count": (I, [VP]),
+        "ec_mask_shard_count": (I, [VP]),
+        "ec_buf_shard": (S, [VP, I, C.POINTER(ShardInfo), PVP]),
+        "ec_mask_shard": (S, [VP, I, C.POINTER(ShardInfo), PVP]),
         "ec_device_info_get": (S, [C.POINTER(DeviceInfo)]),
         "ec_set_stream": (S, [VP]),
         "ec_get_stream": (VP, []),

@@ -336,6 +336,19 @@ class CellBuffer:
     def device_ptr(self) -> int:
         return lib().ec_buf_device_ptr(self._h) or 0
 
+    def shard_count(self) -> int:
+        """0 for a buffer on one GPU; otherwise the number of row strips it is kept as (erased_cells_b200.init_devices)."""
+        return lib().ec_buf_shard_count(self._h)
+
+    def shards(self) -> list:
+        """[(logical_device, cuda_device, offset, len, device_ptr)] of the strips (one entry for a plain buffer)"""
+        out = []
+        for g in range(max(1, self.shard_count())):
+            info = _lib.ShardInfo()
+            check(lib().ec_buf_shard(self._h, g, C.byref(info), None))
+            out.append((info.logical_device, info.cuda_device, info.offset, info.len, info.device_ptr or 0))
+        return out
+
     def get(self, index: int) -> CellValue:
         v = Value()
         check(lib().ec_buf_get(self._h, index, C.byref(v)))

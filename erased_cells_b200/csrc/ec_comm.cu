@@ -30,6 +30,9 @@ struct Nccl {
     void* h = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
@@ -52,6 +55,9 @@ static ec_status nccl_load() {
     if (!g_nccl.field) { set_error("NCCL symbol %s missing", name); return EC_NCCL; }
     SYM(GetUniqueId, "ncclGetUniqueId")
     SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommInitAll, "ncclCommInitAll")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
     SYM(CommDestroy, "ncclCommDestroy")
     SYM(AllReduce, "ncclAllReduce")
     SYM(AllGather, "ncclAllGather")
@@ -63,6 +69,29 @@ static ec_status nccl_load() {
 static ec_status nccl_fail(ncclResult_t r, const char* what) {
     set_error("%s: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl error");
     return EC_NCCL;
+}
+
+// One process driving several GPUs (ec_init_devices): communicators over its own devices, made on first use.
+static ncclComm_t g_local_comms[kMaxDev];
+static int g_local_n = 0;
+ec_status local_allreduce_min_i64(const int* cuda_devices, int n, int64_t* const* device_bufs, const cudaStream_t* streams, size_t count) {
+    if (ec_status s = nccl_load()) return s;
+    {
+        std::lock_guard<std::mutex> lk(g_nccl_mu);
+        if (g_local_n == 0) {
+            if (ncclResult_t r = g_nccl.CommInitAll(g_local_comms, n, cuda_devices)) return nccl_fail(r, "ncclCommInitAll");
+            g_local_n = n;
+        }
+    }
+    if (n != g_local_n) { set_error("invalid argument: the local communicators span %d devices", g_local_n); return EC_INVALID_ARG; }
+    if (ncclResult_t r = g_nccl.GroupStart()) return nccl_fail(r, "ncclGroupStart");
+    for (int g = 0; g < n; ++g)
+        if (ncclResult_t r = g_nccl.AllReduce(device_bufs[g], device_bufs[g], count, ncclInt64, ncclMin, g_local_comms[g], streams[g])) {
+            g_nccl.GroupEnd();
+            return nccl_fail(r, "ncclAllReduce(min)");
+        }
+    if (ncclResult_t r = g_nccl.GroupEnd()) return nccl_fail(r, "ncclGroupEnd");
+    return EC_OK;
 }
 }  // namespace ec
 
@@ -78,32 +107,41 @@ ec_status ec_comm_unique_id(void* id128) {
     memcpy(id128, &id, 128);
     return EC_OK;
 }
-// Map every rank's mailbox into this process: cudaIpc handles travel through an NCCL all-gather.
+// Map every rank's mailbox into this process: cudaIpc handles travel through an NCCL all-gather. Every rank runs the
+// same collectives whatever happens locally — a rank that could not allocate, export or map sends a zeroed handle and
+// votes 0 in the final MIN all-reduce, so all ranks agree on peer_ok and nobody is left waiting inside a collective.
 static ec_status peer_setup(ec_comm* c) {
     c->peer_ok = false;
-    if (c->n_ranks > 32 || env_int("EC_NO_PEER_EXCHANGE", 0)) return EC_OK;  // one warp folds the ranks; NCCL path otherwise
+    if (c->n_ranks > 32 || env_int("EC_NO_PEER_EXCHANGE", 0)) return EC_OK;  // one warp folds the ranks; NCCL path otherwise (same decision on every rank)
     cudaStream_t st = static_cast<cudaStream_t>(ec_get_stream());
     const size_t words = size_t(2) * c->n_ranks * 4;
-    if (cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->mailbox), words * 8)) return cuda_fail(e, "cudaMalloc(mailbox)");
-    if (cudaError_t e = cudaMemset(c->mailbox, 0, words * 8)) return cuda_fail(e, "cudaMemset(mailbox)");
+    int ok = 1;
     cudaIpcMemHandle_t mine;
-    if (cudaIpcGetMemHandle(&mine, c->mailbox) != cudaSuccess) { cudaGetLastError(); return EC_OK; }
+    memset(&mine, 0, sizeof mine);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (cudaMalloc(reinterpret_cast<void**>(&c->mailbox), words * 8) != cudaSuccess || cudaMemset(c->mailbox, 0, words * 8) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine, c->mailbox) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+        memset(&mine, 0, sizeof mine);
+    }
     char* dh = nullptr;
     if (cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&dh), size_t(64) * (c->n_ranks + 1))) return cuda_fail(e, "cudaMalloc");
+    struct Free { char* p; ~Free() { cudaFree(p); } } free_dh{dh};
     if (cudaError_t e = cudaMemcpyAsync(dh, &mine, 64, cudaMemcpyHostToDevice, st)) return cuda_fail(e, "cudaMemcpyAsync");
     if (ncclResult_t r = g_nccl.AllGather(dh, dh + 64, 64, ncclChar, c->comm, st)) return nccl_fail(r, "ncclAllGather(ipc handles)");
     cudaIpcMemHandle_t all[64];
     if (cudaError_t e = cudaMemcpyAsync(all, dh + 64, size_t(64) * c->n_ranks, cudaMemcpyDeviceToHost, st)) return cuda_fail(e, "cudaMemcpyAsync");
     if (cudaError_t e = cudaStreamSynchronize(st)) return cuda_fail(e, "cudaStreamSynchronize");
-    cudaFree(dh);
     unsigned long long* ptrs[64];
-    int ok = 1;
+    const cudaIpcMemHandle_t zero{};
     for (int r = 0; r < c->n_ranks; ++r) {
         c->opened[r] = nullptr;
+        ptrs[r] = nullptr;
         if (r == c->rank) { ptrs[r] = c->mailbox; continue; }
+        if (!ok) continue;
         void* p = nullptr;
-        if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        if (memcmp(&all[r], &zero, sizeof zero) == 0 || cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; continue; }
         c->opened[r] = p;
         ptrs[r] = static_cast<unsigned long long*>(p);
     }
@@ -113,7 +151,13 @@ static ec_status peer_setup(ec_comm* c) {
     if (ncclResult_t r = g_nccl.AllReduce(c->dkeys, c->dkeys, 1, ncclInt64, ncclMin, c->comm, st)) return nccl_fail(r, "ncclAllReduce");
     if (cudaError_t e = cudaMemcpyAsync(c->pinned, c->dkeys, 8, cudaMemcpyDeviceToHost, st)) return cuda_fail(e, "cudaMemcpyAsync");
     if (cudaError_t e = cudaStreamSynchronize(st)) return cuda_fail(e, "cudaStreamSynchronize");
-    if (c->pinned[0] != 1) return EC_OK;
+    if (c->pinned[0] != 1) {  // vetoed somewhere: give the mailbox and the mappings back, the NCCL path is used
+        for (int r = 0; r < c->n_ranks; ++r)
+            if (c->opened[r]) { cudaIpcCloseMemHandle(c->opened[r]); c->opened[r] = nullptr; }
+        cudaFree(c->mailbox);
+        c->mailbox = nullptr;
+        return EC_OK;
+    }
     if (cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->peer_ptrs_dev), sizeof(void*) * c->n_ranks)) return cuda_fail(e, "cudaMalloc");
     if (cudaError_t e = cudaMemcpy(c->peer_ptrs_dev, ptrs, sizeof(void*) * c->n_ranks, cudaMemcpyHostToDevice)) return cuda_fail(e, "cudaMemcpy");
     c->peer_ok = true;

@@ -9,25 +9,61 @@
 
 #include "../../include/erased_cells_b200.h"
 
+#include <algorithm>
+#include <atomic>
+#include <functional>
+#include <vector>
+
 namespace ec {
-struct DevBlock;  // refcounted device allocation (returns to the caching allocator when the last user lets go)
-struct Expr;      // a deferred op (lazy mode): evaluated, possibly fused with its children, on first use
+struct Expr;       // a deferred op (lazy mode): evaluated, possibly fused with its children, on first use
+struct CountSlot;  // pinned host slot a mask-producing kernel publishes its popcount into
+
+// Refcounted device allocation. It belongs to one logical device and to the stream it was allocated for (its home
+// stream): kernels that read or write it on another stream are ordered against the home stream by events, and the
+// block goes back to the home stream's free list when its last user lets go (see dev_free in ec_api.cu).
+struct DevBlock {
+    void* p;
+    int dev;
+    cudaStream_t home;
+    std::atomic<int> snapshots{0};       // pending lazy expressions that read this block: in-place mutation copies first
+    std::vector<std::pair<cudaStream_t, int>> foreign;  // other (stream, logical device) that touched the block (guarded by the allocator mutex)
+    DevBlock(void* q, int d, cudaStream_t s) : p(q), dev(d), home(s) {}
+    DevBlock(const DevBlock&) = delete;
+    DevBlock& operator=(const DevBlock&) = delete;
+    ~DevBlock();
+};
 }  // namespace ec
 
+// A CellBuffer is either plain — `len` cells at dptr on logical device `dev` — or row-strip sharded: parts[g] is a
+// plain buffer on logical device g holding cells [offs[g], offs[g + 1]) (possibly none), dptr is null.
 struct ec_buf {
-    uint8_t ct;
-    bool owned;
-    size_t len;
-    size_t capacity_bytes;
-    void* dptr;         // null while `expr` is pending
-    cudaEvent_t ready;  // set by ec_buf_from_host_async: readers on other streams wait on it
+    uint8_t ct = 0;
+    bool owned = true;
+    size_t len = 0;
+    size_t capacity_bytes = 0;
+    void* dptr = nullptr;         // null while `expr` is pending (and for a sharded buffer)
+    cudaEvent_t ready = nullptr;  // set by ec_buf_from_host_async: readers on other streams wait on it
     std::shared_ptr<ec::DevBlock> blk;
     std::shared_ptr<ec::Expr> expr;
+    int dev = 0;
+    std::vector<ec_buf*> parts;
+    std::vector<size_t> offs;
 };
+// Validity bits, packed; plain or sharded like ec_buf. The words are refcounted (a clone shares them until one side is
+// mutated). The number of set bits is cached: kernels that produce a mask count as they go and the last CTA
+// publishes the total into `cnt_slot` (pinned host memory) tagged with `cnt_seq`.
 struct ec_mask {
-    size_t len;
-    size_t capacity_bytes;
-    uint32_t* words;
+    size_t len = 0;
+    size_t capacity_bytes = 0;
+    uint32_t* words = nullptr;
+    std::shared_ptr<ec::DevBlock> blk;
+    int dev = 0;
+    std::shared_ptr<ec::CountSlot> cnt;  // {ones, seq} in pinned host memory; shared by clones
+    uint64_t cnt_seq = 0;                // the tag the producing kernel publishes with (0: nobody is counting)
+    bool cnt_known = false;
+    uint64_t ones = 0;
+    std::vector<ec_mask*> parts;
+    std::vector<size_t> offs;
 };
 struct ec_event {
     cudaEvent_t ev;
@@ -37,7 +73,84 @@ namespace ec {
 
 struct ReduceScratch;
 struct PeerExchange;
-struct VmProgram;
+struct MaskCount;  // ec_common.cuh: where a mask-producing kernel publishes the number of set bits it wrote
+
+constexpr int kMaxDev = 16;
+enum : int { FINISH_HOST = 0, FINISH_PEER = 1, FINISH_NCCL = 2 };  // how a sharded reduction crosses the GPUs (ec_set_shard_finish)
+
+// ---- logical devices and row-strip sharding inside one process (ec_api.cu / ec_shard.cu) ------------------------
+int n_devices();
+int device_phys(int dev);
+cudaStream_t device_stream(int dev);  // the stream the calling thread's work on logical device `dev` goes to
+// true when a fresh buffer of n cells is to be spread over the devices: several devices, n >= the threshold, and the
+// caller is not already working on one strip
+bool shard_policy(size_t n);
+inline bool is_sharded(const ec_buf* b) { return !b->parts.empty(); }
+inline bool is_sharded(const ec_mask* m) { return !m->parts.empty(); }
+// run plain entry points on logical device `dev` (binds the thread to its CUDA device, turns the sharding policy off)
+struct DevScope {
+    int prev_dev, prev_phys = -1;
+    explicit DevScope(int dev);
+    ~DevScope();
+    DevScope(const DevScope&) = delete;
+    DevScope& operator=(const DevScope&) = delete;
+};
+// a reduction in flight whose finishing CTA publishes {r0, r1, seq, status} into mapped pinned host memory
+struct PendingReduce {
+    volatile uint64_t* pin = nullptr;
+    uint64_t seq = 0;
+    cudaStream_t stream = nullptr;
+    int dev = 0;
+};
+ec_status reduce_end(const PendingReduce& p, uint64_t* r0, uint64_t* r1);
+// statistics kernels in flight: raw accumulators arrive in pinned host memory once `stream` has drained
+struct StatsPending {
+    uint64_t* pin = nullptr;
+    cudaStream_t stream = nullptr;
+    int dev = 0;
+    int words = 0;
+};
+// begin = enqueue on the calling thread's current device and return; end = wait for the result
+ec_status min_max_begin(const ec_buf* b, const ec_mask* m, const PeerExchange* px, PendingReduce* pend, ReduceScratch* sc_out);
+ec_status popcount_begin(const ec_mask* m, const PeerExchange* px, uint64_t second_word, PendingReduce* pend);
+ec_status first_diff_begin(const ec_buf* l, const ec_buf* r, size_t n, PendingReduce* pend);
+ec_status mask_first_diff(const ec_mask* l, const ec_mask* r, size_t n, uint64_t* bit_out);
+ec_status int_stats_begin(const ec_buf* b, const ec_mask* m, StatsPending* p);
+ec_status moments_begin(const ec_buf* b, const ec_mask* m, double pivot, int exp2, StatsPending* p);
+ec_status stats_end(const StatsPending& p, uint64_t* w);
+bool stats_integer_route(uint8_t ct);
+void int_stats_min_max(uint8_t ct, const uint64_t* w, ec_value* mn, ec_value* mx);
+ec_status mask_ones(const ec_mask* m, uint64_t* ones);
+// all-reduce(MIN) of `count` int64 per device over the GPUs of this process (ncclCommInitAll communicators, ec_comm.cu)
+ec_status local_allreduce_min_i64(const int* cuda_devices, int n, int64_t* const* device_bufs, const cudaStream_t* streams, size_t count);
+
+// ---- sharded flavours of the entry points (ec_shard.inc) ---------------------------------------------------------
+using GenFn = std::function<ec_status(size_t off, size_t n, ec_buf** out)>;
+using MaskGenFn = std::function<ec_status(size_t off, size_t n, ec_mask** out)>;
+using Map1Fn = std::function<ec_status(const ec_buf*, ec_buf**)>;
+using Map2Fn = std::function<ec_status(const ec_buf*, const ec_buf*, ec_buf**)>;
+using MapBmFn = std::function<ec_status(const ec_buf*, const ec_mask*, ec_buf**)>;
+using BufToMaskFn = std::function<ec_status(const ec_buf*, ec_mask**)>;
+using MaskMap2Fn = std::function<ec_status(const ec_mask*, const ec_mask* /* may be null */, ec_mask**)>;
+int sh_part_of(const std::vector<size_t>& offs, size_t index);
+ec_status sh_generate(uint8_t ct, size_t len, const GenFn& fn, ec_buf** out);
+ec_status shm_generate(size_t len, const MaskGenFn& fn, ec_mask** out);
+ec_status sh_from_host(uint8_t ct, const void* host, size_t len, bool async, ec_buf** out);
+ec_status sh_to_host(const ec_buf* b, void* host);
+ec_status sh_view(const ec_buf* b, size_t off, size_t len, ec_buf** out);
+ec_status shm_slice(const ec_mask* m, size_t off, size_t len, ec_mask** out);
+ec_status sh_map1(const ec_buf* b, uint8_t out_ct, const Map1Fn& fn, ec_buf** out);
+ec_status sh_map2(const ec_buf* l, const ec_buf* r, size_t n, uint8_t out_ct, const Map2Fn& fn, ec_buf** out);
+ec_status sh_map_bm(const ec_buf* b, const ec_mask* m, uint8_t out_ct, const MapBmFn& fn, ec_buf** out);
+ec_status sh_buf_to_mask(const ec_buf* b, const BufToMaskFn& fn, ec_mask** out);
+ec_status shm_map2(const ec_mask* l, const ec_mask* r, size_t n, const MaskMap2Fn& fn, ec_mask** out);
+ec_status sh_masked_binary(int op, const ec_buf* lb, const ec_mask* lm, const ec_buf* rb, const ec_mask* rm, size_t n,
+                           ec_buf** out_buf, ec_mask** out_mask);
+ec_status sh_min_max(const ec_buf* b, const ec_mask* m, uint64_t* k0, uint64_t* k1);
+ec_status sh_first_diff(const ec_buf* l, const ec_buf* r, size_t n, uint64_t* idx);
+ec_status shm_first_diff(const ec_mask* l, const ec_mask* r, size_t n, uint64_t* bit);
+ec_status sh_moments(const ec_buf* b, const ec_mask* m, double pivot, int exp2, uint64_t* raw);
+ec_status sh_statistics(const ec_buf* b, const ec_mask* m, ec_statistics* out);
 
 struct Launch {  // launch context handed to every launcher
     cudaStream_t stream;
@@ -80,7 +193,7 @@ inline cudaError_t launch_k(const Launch& L, void (*kernel)(P...), int grid, int
 // ---- launchers (each TU instantiates its kernel family) ----------------------------------------
 // binary: out[i] = (f64)l[i] op (f64)r[i]; optional fused mask AND
 cudaError_t launch_binary(const Launch& L, int op, int lct, const void* l, int rct, const void* r, double* out,
-                          size_t n, const uint32_t* lm, const uint32_t* rm, uint32_t* om);
+                          size_t n, const uint32_t* lm, const uint32_t* rm, uint32_t* om, const MaskCount& mc);
 cudaError_t launch_scalar(const Launch& L, int op, int lct, const void* l, double s, double* out, size_t n);
 cudaError_t launch_neg(const Launch& L, int ct, const void* a, void* out, size_t n);
 cudaError_t launch_convert(const Launch& L, int sct, const void* a, int dct, void* out, size_t n);
@@ -95,7 +208,6 @@ cudaError_t launch_binary_scalar(const Launch& L, int op1, int lct, const void* 
 cudaError_t launch_binary_scalar_static(const Launch& L, int op1, int lct, const void* l, int rct, const void* r, int op2,
                                         double s, double* out, size_t n);
 cudaError_t launch_scalar_scalar(const Launch& L, int op1, int ct, const void* a, double s1, int op2, double s2, double* out, size_t n);
-cudaError_t launch_vm(const Launch& L, const VmProgram& p, double* out, size_t n);
 // run-time specialised kernel of one pending expression (ec_jit.cu): `expr` is straight-line C over v0.. (operands as
 // f64) and c0.. (scalars) built from ecj_add/sub/mul/div calls. Returns 0 = launched (*err = launch status),
 // 1 = not available (no NVRTC / build failed; ec_last_error says why) -> the caller evaluates op by op.
@@ -125,9 +237,9 @@ cudaError_t launch_first_diff(const Launch& L, int cell_bytes, const void* a, co
                               const ReduceScratch& s);
 // masks
 cudaError_t launch_mask_build(const Launch& L, int cell_bytes, const void* a, size_t n, uint64_t sentinel_bits,
-                              bool pack_bools, uint32_t* out);
+                              bool pack_bools, uint32_t* out, const MaskCount& mc);
 cudaError_t launch_mask_unpack(const Launch& L, const uint32_t* m, size_t n, uint8_t* out);
-cudaError_t launch_mask_bitop(const Launch& L, int mop, const uint32_t* l, const uint32_t* r, size_t n, uint32_t* out);
+cudaError_t launch_mask_bitop(const Launch& L, int mop, const uint32_t* l, const uint32_t* r, size_t n, uint32_t* out, const MaskCount& mc);
 cudaError_t launch_mask_fill(const Launch& L, uint32_t* out, size_t n, bool value);
 cudaError_t launch_synth(const Launch& L, int ct, void* out, size_t n, uint64_t seed, uint64_t index_offset, int kind,
                          double lo, double hi, uint64_t period, uint64_t sentinel_bits);

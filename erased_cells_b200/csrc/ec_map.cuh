@@ -122,13 +122,14 @@ __global__ void __launch_bounds__(THREADS, map2_min_ctas<F>(THREADS)) map2_kerne
                                                        typename F::O* __restrict__ o, size_t n, F f,
                                                        const uint32_t* __restrict__ lm,
                                                        const uint32_t* __restrict__ rm,
-                                                       uint32_t* __restrict__ om) {
+                                                       uint32_t* __restrict__ om, MaskCount mc) {
     using A = typename F::A; using B = typename F::B; using O = typename F::O;
     constexpr int V = VB / cmax<cmax<sizeof(A), sizeof(B)>(), sizeof(O)>();
     constexpr size_t TILE = size_t(THREADS) * V * UNROLL;
     static_assert(TILE % 128 == 0, "a tile must cover whole 16-byte groups of mask words");
     constexpr int TILE_WORDS = TILE / 32;
     const size_t full = n / TILE;
+    unsigned int ones = 0;  // set bits this thread wrote into the result mask
     overlap_prologue();
     for (size_t t = blockIdx.x; t < full; t += gridDim.x) {
         const size_t base = t * TILE + size_t(threadIdx.x) * V;
@@ -153,16 +154,25 @@ __global__ void __launch_bounds__(THREADS, map2_min_ctas<F>(THREADS)) map2_kerne
             st_stream<O, V>(o + base + size_t(u) * THREADS * V, vo);
         }
         if (mask_lane) {
-            *reinterpret_cast<uint4*>(om + t * TILE_WORDS + threadIdx.x * 4) =
-                make_uint4(wl.x & wr.x, wl.y & wr.y, wl.z & wr.z, wl.w & wr.w);
+            const uint4 w = make_uint4(wl.x & wr.x, wl.y & wr.y, wl.z & wr.z, wl.w & wr.w);
+            *reinterpret_cast<uint4*>(om + t * TILE_WORDS + threadIdx.x * 4) = w;
+            ones += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
         }
     }
     if (blockIdx.x == full % gridDim.x) {
         for (size_t i = full * TILE + threadIdx.x; i < n; i += THREADS) o[i] = f(a[i], b[i]);
         if (lm != nullptr) {
             const size_t words = (n + 31) / 32;
-            for (size_t w = full * TILE_WORDS + threadIdx.x; w < words; w += THREADS) om[w] = lm[w] & rm[w];
+            for (size_t w = full * TILE_WORDS + threadIdx.x; w < words; w += THREADS) {
+                const uint32_t x = lm[w] & rm[w];
+                om[w] = x;
+                ones += __popc(x);
+            }
         }
+    }
+    if (lm != nullptr && mc.acc != nullptr) {  // uniform over the grid: Mask::counts of the result comes for free
+        const unsigned long long c = block_count(ones);
+        if (threadIdx.x == 0) publish_count(mc, c);
     }
 }
 

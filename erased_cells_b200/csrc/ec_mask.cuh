@@ -23,13 +23,14 @@ template <int V> __device__ __forceinline__ uint32_t assemble_word(uint32_t bits
 // The ragged tail runs one cell per lane and builds its words with __ballot_sync.
 template <class U, bool PACK_BOOLS, int VB, int UNROLL, int THREADS>
 __global__ void __launch_bounds__(THREADS) mask_build_kernel(const U* __restrict__ a, size_t n, U sentinel,
-                                                             uint32_t* __restrict__ out) {
+                                                             uint32_t* __restrict__ out, MaskCount mc) {
     constexpr int V0 = VB / sizeof(U);
     constexpr int V = V0 > 32 ? 32 : V0;
     constexpr int TPW = 32 / V;
     constexpr size_t TILE = size_t(THREADS) * V * UNROLL;
     const int lane = threadIdx.x & 31;
     const size_t full = n / TILE;
+    unsigned int ones = 0;
     overlap_prologue();
     for (size_t t = blockIdx.x; t < full; t += gridDim.x) {
         const size_t base = t * TILE + size_t(threadIdx.x) * V;
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(THREADS) mask_build_kernel(const U* __restrict
                     bits |= static_cast<uint32_t>(valid) << j;
                 }
             }
+            ones += __popc(bits);
             const uint32_t w = assemble_word<V>(bits, lane);
             if (lane % TPW == 0) out[(base + size_t(u) * THREADS * V) / 32] = w;
         }
@@ -70,7 +72,12 @@ __global__ void __launch_bounds__(THREADS) mask_build_kernel(const U* __restrict
             if (i < n) valid = PACK_BOOLS ? (a[i] != U(0)) : (a[i] != sentinel);
             const uint32_t w = __ballot_sync(0xFFFFFFFFu, valid);
             if (lane == 0) out[i0 / 32] = w;
+            ones += valid ? 1u : 0u;
         }
+    }
+    if (mc.acc != nullptr) {
+        const unsigned long long c = block_count(ones);
+        if (threadIdx.x == 0) publish_count(mc, c);
     }
 }
 
@@ -104,20 +111,27 @@ __device__ __forceinline__ uint32_t mask_word_op(int mop, uint32_t x, uint32_t y
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) mask_bitop_kernel(int mop, const uint32_t* __restrict__ l,
                                                              const uint32_t* __restrict__ r, size_t n,
-                                                             uint32_t* __restrict__ out) {
+                                                             uint32_t* __restrict__ out, MaskCount mc) {
     const size_t words = (n + 31) / 32;
     const size_t groups = words / 4;
+    unsigned int ones = 0;
     overlap_prologue();
     for (size_t g = blockIdx.x * size_t(THREADS) + threadIdx.x; g < groups; g += size_t(gridDim.x) * THREADS) {
         Vec<uint32_t, 4> x = ld_stream<uint32_t, 4>(l + 4 * g), y = x, o;
         if (mop != MOP_NOT) y = ld_stream<uint32_t, 4>(r + 4 * g);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) o.v[q] = mask_word_op(mop, x.v[q], y.v[q], 4 * g + q, words, n);
+        for (int q = 0; q < 4; ++q) { o.v[q] = mask_word_op(mop, x.v[q], y.v[q], 4 * g + q, words, n); ones += __popc(o.v[q]); }
         st_stream<uint32_t, 4>(out + 4 * g, o);
     }
     if (blockIdx.x == 0 && threadIdx.x < words % 4) {
         const size_t w = groups * 4 + threadIdx.x;
-        out[w] = mask_word_op(mop, l[w], mop == MOP_NOT ? 0u : r[w], w, words, n);
+        const uint32_t x = mask_word_op(mop, l[w], mop == MOP_NOT ? 0u : r[w], w, words, n);
+        out[w] = x;
+        ones += __popc(x);
+    }
+    if (mc.acc != nullptr) {
+        const unsigned long long c = block_count(ones);
+        if (threadIdx.x == 0) publish_count(mc, c);
     }
 }
 

@@ -29,7 +29,8 @@ struct ReduceScratch {
     uint64_t* partials;     // 2 * max_blocks
     unsigned int* ticket;   // zero between launches (the finishing CTA resets it)
     uint64_t* result;       // 4 words: [0..1] raw result; [2..3] min_max as {skey(min), ~skey(max)} for a MIN all-reduce
-    uint64_t* host_result;  // optional device alias of mapped pinned host memory: {r0, r1, epoch or 1, status}; saves the D2H copy
+    uint64_t* host_result;  // optional device alias of mapped pinned host memory: {r0, r1, host_seq, status}; saves the D2H copy
+    uint64_t host_seq;      // tag written last into host_result[2]: the host polls for it instead of synchronising the stream
     PeerExchange px;
 };
 
@@ -139,12 +140,13 @@ __device__ __forceinline__ void block_finish(uint64_t k0, uint64_t k1, uint64_t 
             s.result[2] = a0 ^ 0x8000000000000000ull;
             s.result[3] = ~(a1 ^ 0x8000000000000000ull);
         }
-        if (s.host_result != nullptr) {  // mapped pinned memory: the host reads it after a stream sync, no D2H copy
-            s.host_result[0] = a0;
-            s.host_result[1] = a1;
-            s.host_result[3] = xstatus;
+        if (s.host_result != nullptr) {  // mapped pinned memory: the host polls word 2 for its tag, no D2H copy, no stream sync
+            volatile uint64_t* hr = s.host_result;
+            hr[0] = a0;
+            hr[1] = a1;
+            hr[3] = xstatus;
             __threadfence_system();
-            s.host_result[2] = s.px.peers != nullptr ? s.px.epoch : 1ull;
+            hr[2] = s.host_seq;
         }
         *s.ticket = 0;  // ready for the next launch on this stream
     }

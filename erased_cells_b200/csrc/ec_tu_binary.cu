@@ -19,20 +19,21 @@ using LT = type_of<EC_LCT>::type;
 
 template <class F>
 static cudaError_t go2(const Launch& Lc, const typename F::A* l, const typename F::B* r, double* out, size_t n, F f,
-                       const uint32_t* lm, const uint32_t* rm, uint32_t* om) {
+                       const uint32_t* lm, const uint32_t* rm, uint32_t* om, const MaskCount& mc) {
     constexpr int V = EC_VB / cmax<cmax<sizeof(typename F::A), sizeof(typename F::B)>(), sizeof(double)>();
     constexpr size_t TILE = size_t(kThreads) * V * EC_UNROLL;
-    return launch_k(Lc, map2_kernel<F, EC_VB, EC_UNROLL, kThreads>, grid_for(n, TILE, Lc), kThreads, l, r, out, n, f, lm, rm, om);
+    return launch_k(Lc, map2_kernel<F, EC_VB, EC_UNROLL, kThreads>, grid_for(n, TILE, Lc), kThreads, l, r, out, n, f, lm, rm, om, mc);
 }
+static const MaskCount kNoCount{nullptr, nullptr, 0};
 
 template <class R>
 static cudaError_t binary_r(const Launch& Lc, int op, const LT* l, const R* r, double* out, size_t n,
-                            const uint32_t* lm, const uint32_t* rm, uint32_t* om) {
+                            const uint32_t* lm, const uint32_t* rm, uint32_t* om, const MaskCount& mc) {
     switch (op) {
-        case OP_ADD: return go2(Lc, l, r, out, n, BinaryF<LT, R, OP_ADD>{}, lm, rm, om);
-        case OP_SUB: return go2(Lc, l, r, out, n, BinaryF<LT, R, OP_SUB>{}, lm, rm, om);
-        case OP_MUL: return go2(Lc, l, r, out, n, BinaryF<LT, R, OP_MUL>{}, lm, rm, om);
-        case OP_DIV: return go2(Lc, l, r, out, n, BinaryF<LT, R, OP_DIV>{}, lm, rm, om);
+        case OP_ADD: return go2(Lc, l, r, out, n, BinaryF<LT, R, OP_ADD>{}, lm, rm, om, mc);
+        case OP_SUB: return go2(Lc, l, r, out, n, BinaryF<LT, R, OP_SUB>{}, lm, rm, om, mc);
+        case OP_MUL: return go2(Lc, l, r, out, n, BinaryF<LT, R, OP_MUL>{}, lm, rm, om, mc);
+        case OP_DIV: return go2(Lc, l, r, out, n, BinaryF<LT, R, OP_DIV>{}, lm, rm, om, mc);
     }
     return cudaErrorInvalidValue;
 }
@@ -41,9 +42,9 @@ static cudaError_t binary_r(const Launch& Lc, int op, const LT* l, const R* r, d
 #define EC_CAT(a, b) EC_CAT_(a, b)
 
 cudaError_t EC_CAT(launch_binary_l, EC_LCT)(const Launch& Lc, int op, const void* l, int rct, const void* r, double* out,
-                                            size_t n, const uint32_t* lm, const uint32_t* rm, uint32_t* om) {
+                                            size_t n, const uint32_t* lm, const uint32_t* rm, uint32_t* om, const MaskCount& mc) {
     switch (rct) {
-#define X(id, p) case id: return binary_r<p>(Lc, op, static_cast<const LT*>(l), static_cast<const p*>(r), out, n, lm, rm, om);
+#define X(id, p) case id: return binary_r<p>(Lc, op, static_cast<const LT*>(l), static_cast<const p*>(r), out, n, lm, rm, om, mc);
         EC_WITH_CT(X)
 #undef X
     }
@@ -52,7 +53,7 @@ cudaError_t EC_CAT(launch_binary_l, EC_LCT)(const Launch& Lc, int op, const void
 
 cudaError_t EC_CAT(launch_normdiff_l, EC_LCT)(const Launch& Lc, const void* l, int rct, const void* r, double* out, size_t n) {
     switch (rct) {
-#define X(id, p) case id: return go2(Lc, static_cast<const LT*>(l), static_cast<const p*>(r), out, n, NormDiffF<LT, p>{}, nullptr, nullptr, nullptr);
+#define X(id, p) case id: return go2(Lc, static_cast<const LT*>(l), static_cast<const p*>(r), out, n, NormDiffF<LT, p>{}, nullptr, nullptr, nullptr, kNoCount);
         EC_WITH_CT(X)
 #undef X
     }
@@ -62,7 +63,7 @@ cudaError_t EC_CAT(launch_normdiff_l, EC_LCT)(const Launch& Lc, const void* l, i
 cudaError_t EC_CAT(launch_binary_scalar_l, EC_LCT)(const Launch& Lc, int op1, const void* l, int rct, const void* r, int op2,
                                                    double s, double* out, size_t n) {
     switch (rct) {
-#define X(id, p) case id: return go2(Lc, static_cast<const LT*>(l), static_cast<const p*>(r), out, n, BinaryScalarF<LT, p>{op1, op2, s}, nullptr, nullptr, nullptr);
+#define X(id, p) case id: return go2(Lc, static_cast<const LT*>(l), static_cast<const p*>(r), out, n, BinaryScalarF<LT, p>{op1, op2, s}, nullptr, nullptr, nullptr, kNoCount);
         EC_WITH_CT(X)
 #undef X
     }

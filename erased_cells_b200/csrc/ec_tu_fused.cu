@@ -3,7 +3,6 @@
 // run the runtime-op functor of ec_tu_binary.cu (same results, ~1.4x the instructions).
 #include "ec_internal.hpp"
 #include "ec_map.cuh"
-#include "ec_vm.cuh"
 
 #ifndef EC_VB
 #define EC_VB 32
@@ -20,7 +19,7 @@ static cudaError_t go(const Launch& Lc, const void* l, const void* r, double s, 
     constexpr int V = EC_VB / cmax<cmax<sizeof(L), sizeof(R)>(), 8>();
     constexpr size_t TILE = size_t(kThreads) * V * EC_UNROLL;
     return launch_k(Lc, map2_kernel<F, EC_VB, EC_UNROLL, kThreads>, grid_for(n, TILE, Lc), kThreads,
-                    static_cast<const L*>(l), static_cast<const R*>(r), out, n, F{s}, nullptr, nullptr, nullptr);
+                    static_cast<const L*>(l), static_cast<const R*>(r), out, n, F{s}, nullptr, nullptr, nullptr, MaskCount{nullptr, nullptr, 0});
 }
 template <class L, class R, int OP1>
 static cudaError_t by_op2(const Launch& Lc, int op2, const void* l, const void* r, double s, double* out, size_t n) {
@@ -85,12 +84,6 @@ cudaError_t launch_scalar_scalar(const Launch& Lc, int op1, int ct, const void* 
 #undef X
     }
     return cudaErrorInvalidValue;
-}
-
-cudaError_t launch_vm(const Launch& Lc, const VmProgram& p, double* out, size_t n) {
-    constexpr size_t TILE = size_t(kThreads) * EC_VM_V;
-    vm_kernel<kThreads><<<grid_for(n, TILE, Lc), kThreads, 0, Lc.stream>>>(p, out, n);
-    return cudaGetLastError();
 }
 
 }  // namespace ec

@@ -102,29 +102,29 @@ cudaError_t launch_first_diff(const Launch& Lc, int cell_bytes, const void* a, c
 }
 
 template <class U, bool PACK>
-static cudaError_t mask_build_u(const Launch& Lc, const void* a, size_t n, uint64_t sentinel, uint32_t* out) {
+static cudaError_t mask_build_u(const Launch& Lc, const void* a, size_t n, uint64_t sentinel, uint32_t* out, const MaskCount& mc) {
     constexpr int V0 = EC_VB / sizeof(U);
     constexpr int V = V0 > 32 ? 32 : V0;
     constexpr size_t TILE = size_t(kThreads) * V * EC_RUNROLL;
     return launch_k(Lc, mask_build_kernel<U, PACK, EC_VB, EC_RUNROLL, kThreads>, grid_for(n, TILE, Lc), kThreads,
-                    static_cast<const U*>(a), n, static_cast<U>(sentinel), out);
+                    static_cast<const U*>(a), n, static_cast<U>(sentinel), out, mc);
 }
 cudaError_t launch_mask_build(const Launch& Lc, int cell_bytes, const void* a, size_t n, uint64_t sentinel_bits,
-                              bool pack_bools, uint32_t* out) {
-    if (pack_bools) return mask_build_u<uint8_t, true>(Lc, a, n, 0, out);
+                              bool pack_bools, uint32_t* out, const MaskCount& mc) {
+    if (pack_bools) return mask_build_u<uint8_t, true>(Lc, a, n, 0, out, mc);
     switch (cell_bytes) {
-        case 1: return mask_build_u<uint8_t, false>(Lc, a, n, sentinel_bits, out);
-        case 2: return mask_build_u<uint16_t, false>(Lc, a, n, sentinel_bits, out);
-        case 4: return mask_build_u<uint32_t, false>(Lc, a, n, sentinel_bits, out);
-        default: return mask_build_u<uint64_t, false>(Lc, a, n, sentinel_bits, out);
+        case 1: return mask_build_u<uint8_t, false>(Lc, a, n, sentinel_bits, out, mc);
+        case 2: return mask_build_u<uint16_t, false>(Lc, a, n, sentinel_bits, out, mc);
+        case 4: return mask_build_u<uint32_t, false>(Lc, a, n, sentinel_bits, out, mc);
+        default: return mask_build_u<uint64_t, false>(Lc, a, n, sentinel_bits, out, mc);
     }
 }
 cudaError_t launch_mask_unpack(const Launch& Lc, const uint32_t* m, size_t n, uint8_t* out) {
     mask_unpack_kernel<kThreads><<<grid_for(n, size_t(kThreads) * 16, Lc), kThreads, 0, Lc.stream>>>(m, n, out);
     return cudaGetLastError();
 }
-cudaError_t launch_mask_bitop(const Launch& Lc, int mop, const uint32_t* l, const uint32_t* r, size_t n, uint32_t* out) {
-    return launch_k(Lc, mask_bitop_kernel<kThreads>, grid_for((n + 127) / 128, kThreads, Lc), kThreads, mop, l, r, n, out);
+cudaError_t launch_mask_bitop(const Launch& Lc, int mop, const uint32_t* l, const uint32_t* r, size_t n, uint32_t* out, const MaskCount& mc) {
+    return launch_k(Lc, mask_bitop_kernel<kThreads>, grid_for((n + 127) / 128, kThreads, Lc), kThreads, mop, l, r, n, out, mc);
 }
 cudaError_t launch_mask_fill(const Launch& Lc, uint32_t* out, size_t n, bool value) {
     return launch_k(Lc, mask_fill_kernel<kThreads>, grid_for((n + 31) / 32, kThreads, Lc), kThreads, out, n, value ? 0xFFFFFFFFu : 0u);

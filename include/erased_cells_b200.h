@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define EC_ABI_VERSION 1
+#define EC_ABI_VERSION 2
 
 /* Error conventions — src/error.rs:12-27. Only NarrowingError is reachable from the hot path
  * (src/buffer.rs:155-159, src/value.rs:77-81); index panics (src/lib.rs:136-147) and the
@@ -92,6 +92,7 @@ enum { EC_STATS_REGULAR = 0, EC_STATS_EMPTY = 1, EC_STATS_NONFINITE = 2 };
 typedef struct ec_buf ec_buf;   /* CellBuffer: typed cells in HBM */
 typedef struct ec_mask ec_mask; /* Mask: validity bits in HBM, packed 32 cells per little-endian word */
 typedef struct ec_event ec_event;
+typedef struct ec_shard_info ec_shard_info;
 typedef struct ec_comm ec_comm;
 
 typedef struct ec_device_info {
@@ -109,6 +110,21 @@ const char* ec_last_error(void);
 /* src/error.rs:14: the {src, dst} of the last EC_NARROWING on this thread */
 void ec_last_narrowing(uint8_t* src, uint8_t* dst);
 ec_status ec_init(int device);           /* bind this process to one GPU; idempotent */
+/* One process, several GPUs (the reference's caller is one process and one CellBuffer is the whole raster,
+ * src/buffer.rs:52, src/lib.rs:104-163): bind the library to `n` (1..16) CUDA devices. From then on a buffer or mask of
+ * at least ec_set_shard_min_cells() cells is kept as n row strips, strip g on devices[g], and every entry point below
+ * works on it unchanged: maps, casts and mask logic strip by strip with no data-path collective, reductions finishing
+ * across the GPUs. Without a call, the first use binds $EC_DEVICES ("0,1,2,3"), else $EC_DEVICE, else $LOCAL_RANK, else 0.
+ * The same CUDA device may be listed more than once (that is how the sharded paths are tested on a one-GPU box). */
+ec_status ec_init_devices(const int* devices, int n);
+int ec_device_count(void);               /* devices bound so far (0 before the first use) */
+/* threshold (cells) from which new buffers / masks are sharded; default 2^24, $EC_SHARD_MIN_CELLS. Returns the previous value. */
+size_t ec_set_shard_min_cells(size_t cells);
+/* How a sharded reduction crosses the GPUs: 0 the host folds the strips' 16-byte partials out of mapped pinned memory
+ * (default); 1 the finishing CTAs exchange them GPU to GPU through peer-mapped mailboxes, one kernel per GPU and nothing
+ * else; 2 ncclAllReduce over ncclCommInitAll communicators. Identical bits either way (integer keys, exact integer sums).
+ * $EC_SHARD_FINISH = host | peer | nccl. Returns the previous mode, -1 for a bad one. */
+int ec_set_shard_finish(int mode);
 ec_status ec_device_info_get(ec_device_info* out);
 ec_status ec_set_stream(void* cuda_stream); /* NULL restores the library's own stream */
 void* ec_get_stream(void);
@@ -216,9 +232,8 @@ ec_status ec_statistics_finish(const uint64_t* raws, size_t n_parts, const ec_va
  * pending result over refcounted snapshots of their operands; the first access evaluates it, fusing
  * `(X - Y) / (X + Y)`, `(X op1 Y) op2 scalar` and `(X op1 s1) op2 s2` into one pass over HBM. Results are bit-identical to eager
  * evaluation; later put/extend on an operand do not affect a pending result (copy on write).
- * ec_set_lazy(2) additionally sends longer chains through the expression VM (one interpreted pass, ec_vm.cuh) —
- * experimental: bit-identical, but measured only 1.1x faster than op-by-op evaluation on an 8-op chain.
- * ec_set_lazy(3) instead compiles such a chain (up to 8 operands, 8 scalars, 48 ops) into ONE streaming kernel
+ * (mode 2, the interpreted expression VM of ABI 1, is gone: it ran at 0.13 of the HBM roofline; EC_INVALID_ARG.)
+ * ec_set_lazy(3) compiles a longer chain (up to 8 operands, 8 scalars, 48 ops) into ONE streaming kernel
  * specialised at run time with NVRTC (ec_jit.cu): same geometry, rounding and NaN rule as the eager kernels, cached
  * by shape (scalars are kernel parameters). Without libnvrtc the chain is evaluated op by op (same bits). */
 ec_status ec_set_lazy(int mode);
@@ -279,7 +294,23 @@ ec_status ec_buf_fill_nodata(const ec_buf* b, const ec_mask* m, uint8_t dst_ct, 
 ec_status ec_masked_binary(int op, const ec_buf* lbuf, const ec_mask* lmask, const ec_buf* rbuf,
                            const ec_mask* rmask, ec_buf** out_buf, ec_mask** out_mask);
 
-/* ---- row-strip sharding across GPUs (no reference counterpart) ----------------- */
+/* ---- row-strip sharding across GPUs (no reference counterpart) -----------------
+ * Two ways to use several GPUs. (1) One process: ec_init_devices(); buffers are sharded behind the same handles and
+ * nothing else changes (ec_buf_shard* below only look inside). (2) One process per GPU (torchrun): every rank holds
+ * its strip as a plain buffer and finishes reductions with ec_comm_* / ec_*_sharded. */
+/* the strips of a handle: 0 for a plain buffer / mask */
+int ec_buf_shard_count(const ec_buf* b);
+int ec_mask_shard_count(const ec_mask* m);
+struct ec_shard_info {
+    int logical_device;  /* index into the list given to ec_init_devices */
+    int cuda_device;
+    size_t offset, len;  /* cells [offset, offset + len) of the whole raster */
+    void* device_ptr;    /* cells of the strip (mask: its packed words) on cuda_device */
+};
+/* strip `shard` (0 for a plain handle): where it lives and, if `strip` is given, a BORROWED plain handle of it that
+ * stays valid as long as the parent and may be passed to any entry point (the work then runs on the strip's GPU) */
+ec_status ec_buf_shard(const ec_buf* b, int shard, ec_shard_info* info_or_null, const ec_buf** strip_or_null);
+ec_status ec_mask_shard(const ec_mask* m, int shard, ec_shard_info* info_or_null, const ec_mask** strip_or_null);
 /* Strip `shard` of `n_shards` for a width x height row-major raster: whole rows, remainder rows to
  * the last shard, and every strip start a multiple of 128 cells (asserted: width % 128 == 0 or
  * n_shards == 1; otherwise the split falls back to 128-cell aligned cell ranges). */

@@ -23,7 +23,7 @@ def declared_symbols():
 
 def test_library_loads_and_exports_every_declared_symbol():
     L = ec.lib()
-    assert L.ec_abi_version() == 1
+    assert L.ec_abi_version() == 2
     names = declared_symbols()
     assert len(names) > 80
     for n in names:

@@ -428,32 +428,16 @@ def test_concurrent_host_threads(orc):
     assert not errors, errors[:5]
 
 
-def test_lazy_expression_vm_matches_eager(orc):
-    """Longer pending chains run as ONE interpreted pass (ec_vm.cuh); results must be bit-identical to eager, op-by-op
-    evaluation — random expression trees over up to 6 inputs of mixed types, constants, shared sub-expressions,
-    trees too big for the VM (fallback) and operands of different lengths."""
-    L = ec.lib()
+def test_lazy_random_trees_match_eager(orc):
+    """Pending chains through the operators — the precompiled fused shapes (ec.lazy()) and kernels specialised at run
+    time (ec.lazy(jit=True)) — must be bit-identical to eager, op-by-op evaluation: random expression trees over up to
+    6 inputs of mixed types, constants, shared sub-expressions, operands of different lengths, and a chain deep enough
+    to hit the pending-depth cap (evaluated in pieces instead of recursing)."""
     rng = np.random.default_rng(2024)
     n = 2 * 32768 + 37
     types = [CellType.UInt8, CellType.UInt16, CellType.Int16, CellType.Float32, CellType.Float64, CellType.Int64]
     host = [cells(ct, n + (5 if i == 2 else 0), 0x900 + i) for i, ct in enumerate(types)]
     dev = [CellBuffer.from_vec(h) for h in host]
-
-    # EVI = 2.5 * (nir - red) / (nir + 6 * red - 7.5 * blue + 1): 8 ops, 3 inputs, one launch
-    nir, red, blue = dev[1], dev[1 + 1], dev[0]
-    eager = ((nir - red) * 2.5) / (((nir + red * 6.0) - blue * 7.5) + 1.0)
-    with ec.lazy(vm=True):
-        k0 = L.ec_kernel_launches()
-        evi = ((nir - red) * 2.5) / (((nir + red * 6.0) - blue * 7.5) + 1.0)
-        got = evi.to_vec()
-        assert L.ec_kernel_launches() == k0 + 1 and L.ec_last_kernel() == b"expression_vm(lazy)"
-    assert np.array_equal(bits(got), bits(eager.to_vec()))
-    w = orc.tight_binary  # and against the oracle, op by op
-    s = lambda op, a, c: orc.tight_scalar(op, a, orc.value(orc.Float64, c))
-    h_nir, h_red, h_blue = host[1], host[2], host[0]
-    want = w(orc.DIV, s(orc.MUL, w(orc.SUB, h_nir, h_red), 2.5),
-             s(orc.ADD, w(orc.SUB, w(orc.ADD, h_nir, s(orc.MUL, h_red, 6.0)), s(orc.MUL, h_blue, 7.5)), 1.0))
-    assert np.array_equal(bits(got), bits(want))
 
     def build(depth, leaves):
         """random tree; returns a function evaluating it on a list of buffers"""
@@ -472,26 +456,29 @@ def test_lazy_expression_vm_matches_eager(orc):
         leaves = int(rng.integers(1, 7))
         f = build(int(rng.integers(2, 6)), leaves)
         e = f(dev)
-        for mode in (dict(vm=True), dict(), dict(jit=True)):
+        for mode in (dict(), dict(jit=True)):
             with ec.lazy(**mode):
                 lz = f(dev)
                 assert lz == e, (trial, mode)          # device-side bitwise comparison forces the evaluation
     # shared sub-expression: evaluated once, used by two parents and by the user
-    with ec.lazy(vm=True):
+    with ec.lazy():
         num = dev[1] - dev[2]
         a = (num * 2.0 + dev[0]) / (num - 1.0)
         b = num / 3.0
         ea = ((dev[1] - dev[2]) * 2.0 + dev[0]) / ((dev[1] - dev[2]) - 1.0)
     assert a == ea and b == (dev[1] - dev[2]) / 3.0 and num == dev[1] - dev[2]
-    # a chain far longer than the VM's code space falls back (still right, just more launches)
-    with ec.lazy(vm=True):
-        x = dev[3]
-        for i in range(60):
-            x = x * 1.0001 + dev[4]
-    y = dev[3]
-    for i in range(60):
-        y = y * 1.0001 + dev[4]
-    assert x == y
+    # a chain of 600 pending ops: deeper than the cap on pending depth, so it is evaluated in pieces as it is built
+    for mode in (dict(), dict(jit=True)):
+        with ec.lazy(**mode):
+            x = dev[3]
+            for i in range(300):
+                x = x * 1.0001 + dev[4]
+        y = dev[3]
+        for i in range(300):
+            y = y * 1.0001 + dev[4]
+        assert x == y
+    # the interpreted expression VM of ABI 1 is gone
+    assert ec.lib().ec_set_lazy(2) == ec._lib.EC_INVALID_ARG
 
 
 def test_lazy_jit_specialised_kernels_match_eager(orc):

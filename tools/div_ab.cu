@@ -42,7 +42,7 @@ template <class F> static float run(const typename F::A* a, const typename F::B*
     constexpr size_t TILE = size_t(256) * V * 4;
     const int grid = int(n / TILE ? n / TILE : 1);
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < iters; ++i) map2_kernel<F, 32, 4, 256><<<grid, 256>>>(a, b, o, n, F{}, nullptr, nullptr, nullptr);
+    for (int i = 0; i < iters; ++i) map2_kernel<F, 32, 4, 256><<<grid, 256>>>(a, b, o, n, F{}, nullptr, nullptr, nullptr, MaskCount{nullptr, nullptr, 0});
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms;

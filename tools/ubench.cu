@@ -79,7 +79,7 @@ static void run_map2(const char* op, const typename F::A* a, const typename F::B
     constexpr size_t TILE = size_t(THREADS) * V * UNROLL;
     for (int cm : kCaps) {
         const int grid = grid_of(n, TILE, cm * g_sms);
-        float ms = time_ms([&] { ++g_it; map2_kernel<F, VB, UNROLL, THREADS><<<grid, THREADS>>>(rot(a, n, g_arena_in), rot(b, n, g_arena_in), rot(o, n, g_arena_out), n, f, lm, rm, om); });
+        float ms = time_ms([&] { ++g_it; map2_kernel<F, VB, UNROLL, THREADS><<<grid, THREADS>>>(rot(a, n, g_arena_in), rot(b, n, g_arena_in), rot(o, n, g_arena_out), n, f, lm, rm, om, MaskCount{nullptr, nullptr, 0}); });
         report(op, VB, UNROLL, THREADS, cm, bpc * n, ms);
     }
 }
@@ -101,7 +101,7 @@ static void run_maskbuild(const char* op, const U* a, size_t n, uint32_t* out, d
     constexpr size_t TILE = size_t(THREADS) * V * UNROLL;
     for (int cm : kCaps) {
         const int grid = grid_of(n, TILE, cm * g_sms);
-        float ms = time_ms([&] { ++g_it; mask_build_kernel<U, false, VB, UNROLL, THREADS><<<grid, THREADS>>>(rot(a, n, g_arena_in), n, U(0x8000), out); });
+        float ms = time_ms([&] { ++g_it; mask_build_kernel<U, false, VB, UNROLL, THREADS><<<grid, THREADS>>>(rot(a, n, g_arena_in), n, U(0x8000), out, MaskCount{nullptr, nullptr, 0}); });
         report(op, VB, UNROLL, THREADS, cm, bpc * n, ms);
     }
 }

@@ -85,7 +85,7 @@ static void compare(const char* name, const typename F::A* a, const typename F::
     const int iters = n >= (size_t(1) << 28) ? 5 : 40;
     float tl = 0, tp = 0;
     for (int rep = 0; rep < 4; ++rep) {  // alternate; the first repetition warms up
-        const float x = timed([&] { map2_kernel<F, 32, 4, 256><<<grid_lib, 256>>>(a, b, o, n, F{}, nullptr, nullptr, nullptr); }, iters);
+        const float x = timed([&] { map2_kernel<F, 32, 4, 256><<<grid_lib, 256>>>(a, b, o, n, F{}, nullptr, nullptr, nullptr, MaskCount{nullptr, nullptr, 0}); }, iters);
         const float y = timed([&] { map2_pipe_kernel<F, 32, UNROLL, 256, MIN_CTAS><<<int(grid_pipe), 256>>>(a, b, o, n, F{}); }, iters);
         if (rep) { tl += x / 3; tp += y / 3; }
     }

@@ -166,7 +166,7 @@ template <class F> static void all(const char* op, const typename F::A* a, const
                                    unsigned long long* bad) {
     constexpr size_t TILE0 = size_t(256) * 4 * 4;
     const int grid = int(n / TILE0);
-    float ms = time_ms([&] { map2_kernel<F, 32, 4, 256><<<grid, 256>>>(a, b, ref, n, F{}, nullptr, nullptr, nullptr); });
+    float ms = time_ms([&] { map2_kernel<F, 32, 4, 256><<<grid, 256>>>(a, b, ref, n, F{}, nullptr, nullptr, nullptr, MaskCount{nullptr, nullptr, 0}); });
     printf("%s,direct LDG.256/STG.256 (library kernel),ms=%.4f,GBps=%.1f\n", op, ms, bpc * n / (ms * 1e-3) / 1e9);
     run<F, 4096, 4, false>(op, a, b, o, ref, n, bpc, sms, bad);
     run<F, 4096, 8, false>(op, a, b, o, ref, n, bpc, sms, bad);
