@@ -575,19 +575,13 @@ def other_configs(ec, L, torch, dist, rank, world, barrier, max_over_ranks, peak
     res["c5_ndvi_u16_32768_per_gpu_tile"]["min_max_f64"] = entry(timed(lambda: nd5.min_max(), 3, 1), 8.0 * n5, n5)
 
     # beyond the BASELINE configs: a longer band-math chain through the operators, EVI = 2.5*(nir-red)/(nir+6*red-7.5*blue+1),
-    # 8 ops over three u16 bands — op by op vs. one interpreted pass (expression VM) in lazy mode
+    # 8 ops over three u16 bands — op by op vs. one kernel specialised at run time in lazy mode
     del nir, red, nd5
     ne = 16384 * 16384
     b_nir, b_red, b_blue = [synth.device(CellType.UInt16, ne, 0xEC60 + i, kind=synth.INT_RANGE, lo=100, hi=40000) for i in range(3)]
 
     def evi():
         return ((b_nir - b_red) * 2.5) / (((b_nir + b_red * 6.0) - b_blue * 7.5) + 1.0)
-
-    def evi_lazy():
-        with ec.lazy(vm=True):
-            r = evi()
-            r.device_ptr()
-        return r
 
     def evi_jit():  # the same operators, chain compiled at run time into one streaming kernel (NVRTC build outside the timed calls)
         with ec.lazy(jit=True):
@@ -596,11 +590,9 @@ def other_configs(ec, L, torch, dist, rank, world, barrier, max_over_ranks, peak
         return r
     unfused_bytes = (2 + 2 + 8) + 16 + (2 + 8) + (2 + 8 + 8) + (2 + 8) + 24 + 16 + 24  # per cell, op by op
     res["extra_evi_u16_16384"] = {"unfused_8_ops": entry(timed(evi, 3, 1), float(unfused_bytes) * ne, ne),
-                                  "lazy_expression_vm_1_pass": entry(timed(evi_lazy, 3, 1), 14.0 * ne, ne),
                                   "lazy_specialised_kernel_1_pass": entry(timed(evi_jit, 3, 1), 14.0 * ne, ne, kernel=L.ec_last_kernel().decode()),
-                                  "note": "not a BASELINE config; both are opt-in: ec_set_lazy(2) = expression VM (interpretation overhead eats the traffic it saves), "
-                                          "ec_set_lazy(3) = kernel specialised at run time with NVRTC (falls back to op by op without libnvrtc); "
-                                          "GB/s of the 1-pass lines = 14 B/cell (3 x u16 in, f64 out) / time"}
+                                  "note": "not a BASELINE config; opt-in ec_set_lazy(3) = kernel specialised at run time with NVRTC (falls back to op by op without libnvrtc); "
+                                          "GB/s of the 1-pass line = 14 B/cell (3 x u16 in, f64 out) / time"}
     return res
 
 

@@ -280,25 +280,25 @@ static void dev_release(void* p, int dev, cudaStream_t home, const std::vector<s
 }
 DevBlock::~DevBlock() { dev_release(p, dev, home, &foreign); }
 static std::shared_ptr<DevBlock> own_block(void* p) { return std::make_shared<DevBlock>(p, t_dev, cur_stream()); }
-// The calling thread is about to enqueue work that touches `b` on its current stream.
+// The calling thread is about to enqueue work that touches `b` on its current stream. Blocks are written once (by
+// their producer, on the home stream) and mutated only synchronously (put / extend wait for their copy), so ONE wait
+// per (block, foreign stream) is enough: later uses from the same stream find it registered and cost nothing.
 static inline void use_block(DevBlock* b) {
     if (!b) return;
     const cudaStream_t cur = cur_stream();
     if (b->home == cur) return;
     {
-        PhysGuard g(b->dev);
-        cudaEvent_t ev;
-        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); cudaStreamSynchronize(b->home); }
-        else {
-            cudaEventRecord(ev, b->home);
-            cudaStreamWaitEvent(cur, ev, 0);
-            cudaEventDestroy(ev);
-        }
+        std::lock_guard<std::mutex> lk(g_ctx.dev[b->dev].cache.mu);
+        for (auto& f : b->foreign)
+            if (f.first == cur) return;
+        b->foreign.emplace_back(cur, t_dev);
     }
-    std::lock_guard<std::mutex> lk(g_ctx.dev[b->dev].cache.mu);
-    for (auto& f : b->foreign)
-        if (f.first == cur) return;
-    b->foreign.emplace_back(cur, t_dev);
+    PhysGuard g(b->dev);
+    cudaEvent_t ev;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); cudaStreamSynchronize(b->home); return; }
+    cudaEventRecord(ev, b->home);
+    cudaStreamWaitEvent(cur, ev, 0);
+    cudaEventDestroy(ev);
 }
 // device pointer of a buffer about to be read or written on the current stream: orders the access after an
 // asynchronous upload that may still be in flight on the upload stream, and after its producer on another stream

@@ -40,3 +40,18 @@ def test_sharded_handles_distinct_gpus():
         pytest.skip("needs >= 2 GPUs")
     out = run_check(",".join(str(i) for i in range(min(n, 8))))
     assert "finish_modes=[0, 1, 2]" in out, out  # host fold, peer mailboxes and NCCL all ran
+
+
+@pytest.mark.gpu
+def test_reference_test_suites_on_sharded_handles():
+    """The reference's own tests — the C++ port over include/erased_cells.hpp and the Python port — with EVERY non-empty
+    buffer and mask sharded over two logical devices (threshold 1 cell): the handles must behave exactly like plain ones."""
+    env = dict(os.environ, EC_DEVICES="0,0", EC_SHARD_MIN_CELLS="1")
+    exe = os.path.join(ROOT, "tests", "cpp", "build", "test_reference_port")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "-s"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and " 0 failed" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", os.path.join(ROOT, "tests", "test_gpu_reference_kat.py")],
+                       capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

@@ -23,7 +23,7 @@ chains = {
 for name, (fn, bpc) in chains.items():
     print(name)
     ref = fn()
-    for label, mode in (("eager, op by op", None), ("lazy, precompiled shapes only", dict()), ("lazy + expression VM", dict(vm=True)),
+    for label, mode in (("eager, op by op", None), ("lazy, precompiled shapes only", dict()), 
                         ("lazy + run-time specialised kernel", dict(jit=True))):
         def run():
             if mode is None:

@@ -93,7 +93,7 @@ same((v + v).to_vec(), orc.tight_binary(orc.ADD, v.to_vec(), v.to_vec()), "op on
 for i in (0, 1, sh[1][2] - 1, sh[1][2], n - 1):
     assert a.get(i).bits == int(a_h[i]), i
 c = a.clone()
-c.put(sh[-1][2] + 5, 77)
+c.put(sh[-1][2] + 5, np.uint8(77))
 a2 = a_h.copy(); a2[sh[-1][2] + 5] = 77
 same(c.to_vec(), a2, "put into the last strip")
 same(a.to_vec(), a_h, "clone is deep")
