@@ -36,6 +36,14 @@ CT_NAMES = ["UInt8", "UInt16", "UInt32", "UInt64", "Int8", "Int16", "Int32", "In
 CT_SIZE = [1, 2, 4, 8, 1, 2, 4, 8, 4, 8]
 METRIC = "Gcells/s (CellBuffer ops; HBM GB/s and % of 8 TB/s under roofline)"
 NOMINAL_GBS = 8000.0
+WORKLOAD = ("CellBuffer::convert sweep over all 10x10 CellType pairs (31 casts + 10 clones + 59 NarrowingError) "
+            "on 8192^2-cell buffers, one row strip per GPU")
+
+
+def workload_config(cells):
+    """`config` of the JSON line — the same object from both arms (--impl ours / reference)."""
+    return {"workload": WORKLOAD, "cells_per_buffer": cells, "legal_pairs": 41,
+            "l2": "inputs + outputs of a step (23.3 GB) >> the 126 MB L2; dst-major order, a source is re-read after >= 1 GB of other traffic"}
 
 
 def measured_peak():
@@ -139,6 +147,11 @@ class ClockSampler:
 # reference arm: the reference's CPU algorithm (oracle port: per-cell tagged dispatch) on host cores
 # =================================================================================================
 def run_reference(args, out):
+    """The reference's CPU algorithm for the same workload: oracle port, faithful per-cell tagged path
+    (reference src/buffer.rs:150-167 through src/value.rs:74-98), on all host threads as independent row strips
+    (the reference itself is single-threaded: src/buffer.rs:324-329 has no threads). Each step converts a bounded sample
+    of every source buffer (the path streams: Gcells/s does not depend on the buffer length); a 1-thread figure is
+    printed beside it because that is what the unmodified crate would do."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -162,30 +175,34 @@ def run_reference(args, out):
                     except orc.NarrowingError:
                         pass
 
-    def step():
-        ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    def step(n_threads):
+        ths = [threading.Thread(target=work, args=(t,)) for t in range(n_threads)]
         [t.start() for t in ths]
         [t.join() for t in ths]
 
     for _ in range(args.warmup):
-        step()
+        step(threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        step(threads)
     dt = time.perf_counter() - t0
     cells = len(pairs) * per_thread * threads
     value = cells * args.steps / dt / 1e9
-    sample = f"{len(pairs)} legal pairs x {per_thread} cells x {threads} threads per step (same seeds as the GPU workload)"
+    t1 = time.perf_counter()
+    step(1)
+    one_core = len(pairs) * per_thread / (time.perf_counter() - t1) / 1e9
+    sample = (f"{len(pairs)} legal pairs x {per_thread} cells x {threads} threads per step: the first cells of each thread's row strip of the "
+              f"8192^2 buffers, same seeds as the GPU workload")
     out.emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Gcells/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8..f64 casts (integer/f32/f64)", "data": "synthetic",
-        "config": {"workload": "CellBuffer::convert sweep, all 10x10 CellType pairs, 8192^2-cell buffers (bounded sample per step)",
-                   "cells_per_buffer": SIDE * SIDE, "sample_cells_per_pair_per_step": per_thread * threads},
-        "cpu_baseline": {"value": value, "unit": "Gcells/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": workload_config(SIDE * SIDE),
+        "cpu_baseline": {"value": value, "unit": "Gcells/s", "cores": threads, "kind": "port", "sample": sample,
+                         "one_core_value": one_core, "sample_cells_per_pair_per_step": per_thread * threads},
         "e2e": {"value": value, "unit": "Gcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is Rust (no toolchain in this image): timed the C++ restatement oracle/, faithful per-cell tagged path, "
-                "one independent strip per host thread (the reference itself is single-threaded)",
+                "one independent strip per host thread (the reference itself is single-threaded: one_core_value)",
     })
 
 
@@ -273,6 +290,19 @@ def run_ours(args, out):
                 raise AssertionError("illegal convert did not fail")
             except ec.NarrowingError:
                 pass
+
+    # ---- parity of what is about to be timed: two 64 Ki-cell windows of every legal pair against the oracle -----------
+    parity = {}
+    from oracle import oracle as orc  # the checker (test infrastructure), never the thing measured
+    orc.build()
+    win = 1 << 16
+    ok = True
+    for s_, d_ in pairs:
+        for w0 in (0, cells - win):
+            got = srcs[s_].view(w0, win).convert(CellType(d_)).to_vec()
+            want = orc.tight_convert(synth.host(CellType(s_), win, 0xEC10 + s_, index_offset=rank * cells + w0), d_)
+            ok &= bool(got.dtype == want.dtype and np.array_equal(got.view(np.uint8), want.view(np.uint8)))
+    parity["convert_sweep_sampled_windows_vs_oracle"] = ok
 
     # ---- device-resident timing ------------------------------------------------------------------
     # Region A (value): K steps bracketed by barrier + synchronize, nothing but the sweep inside.
@@ -398,18 +428,36 @@ def run_ours(args, out):
             e2e_step()
         barrier()
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+        # what the host links can do at all, with every rank copying at once: bare pinned cudaMemcpyAsync, 256 MiB blocks,
+        # D2H alone and D2H + H2D together (the e2e step is D2H-bound with the uploads hidden behind it)
+        probe = pcie_probe(torch, barrier, max_over_ranks)
+        d2h_rate = d2h / (e2e_ms * 1e-3) / 1e9
         e2e = {"value": len(pairs) * cells * world / (e2e_ms * 1e-3) / 1e9, "unit": "Gcells/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps,
-               "pcie_GBps_each_way": [round(h2d / (e2e_ms * 1e-3) / 1e9, 2), round(d2h / (e2e_ms * 1e-3) / 1e9, 2)],
+               "pcie_GBps_each_way": [round(h2d / (e2e_ms * 1e-3) / 1e9, 2), round(d2h_rate, 2)],
+               "roofline": {"bound": "pcie_d2h", "achieved": round(d2h_rate, 2), "peak": probe["d2h_GBps_per_rank_all_ranks_busy"], "unit": "GB/s per rank",
+                            "frac": round(d2h_rate / probe["d2h_GBps_per_rank_all_ranks_busy"], 3), "probe": probe,
+                            "note": "peak = this rank's bare D2H rate while all ranks copy at once (the host side is shared); "
+                                    "the step moves d2h_bytes_per_step per rank"},
                "api": "CellBuffer.from_vec(pinned host, wait=False: next source prefetched) -> convert(ct) -> to_vec(pinned host), per rank"}
         for p in keep + [pout]:
             L.ec_host_free(p)
     del srcs
 
+    # ---- strong scaling on the 32768^2 rasters (configs 4 and 5) with the cross-GPU finish, parity asserted ----------
+    strong = None
+    if not args.no_configs:
+        strong = strong_scaling(ec, L, torch, dist, rank, world, local, barrier, max_over_ranks, peak, parity)
+
     # ---- the other BASELINE configs, once each (not the headline) -----------------------------------
     configs = {}
     if not args.no_configs:
         configs = other_configs(ec, L, torch, dist, rank, world, barrier, max_over_ranks, peak)
+    parity_ok = all(parity.values())
+    if world > 1:  # every rank must have seen parity
+        t = torch.tensor([int(parity_ok)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        parity_ok = bool(int(t.item()))
 
     # ---- CPU baseline beside it (rank 0, N == 1): oracle port on a bounded sample ----------------------
     cpu = None
@@ -431,11 +479,9 @@ def run_ours(args, out):
             "metric": METRIC, "value": value, "unit": "Gcells/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8..f64 casts (integer/f32/f64)", "data": "synthetic",
-            "config": {"workload": "CellBuffer::convert sweep over all 10x10 CellType pairs (31 casts + 10 clones + 59 NarrowingError) "
-                                   "on 8192^2-cell buffers, one row strip per GPU",
-                       "cells_per_buffer": cells, "legal_pairs": len(pairs), "l2": "inputs+outputs of a step (%.1f GB) >> %d MB L2; "
-                       "dst-major order, a source is re-read after >= 1 GB of other traffic" % (step_bytes / 1e9, info.l2_bytes >> 20),
-                       "device": info.name.decode(), "sm_count": info.sm_count},
+            "config": workload_config(cells),
+            "device": {"name": info.name.decode(), "sm_count": info.sm_count, "l2_MB": info.l2_bytes >> 20},
+            "parity_ok": parity_ok, "parity": parity, "strong_scaling": strong,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "GBps_algorithmic_step": round(step_bytes * world / (ms_per_step * 1e-3) / 1e9, 1),
             "per_pair": per_pair, "configs": configs,
@@ -443,6 +489,247 @@ def run_ours(args, out):
         out.emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if not parity_ok:
+        raise SystemExit("bench.py: a result differs from the oracle / between ranks: " + json.dumps(parity))
+
+
+def pcie_probe(torch, barrier, max_over_ranks, block=256 << 20, reps=6):
+    """Bare pinned-memory copies on every rank at once (torch copy_ = cudaMemcpyAsync): GB/s per rank, worst rank."""
+    dev = torch.empty(block, dtype=torch.uint8, device="cuda")
+    dev2 = torch.empty(block, dtype=torch.uint8, device="cuda")
+    h_out = torch.empty(block, dtype=torch.uint8).pin_memory()
+    h_in = torch.empty(block, dtype=torch.uint8).pin_memory()
+    side = torch.cuda.Stream()
+
+    def timed(fn):
+        fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        return reps * block / dt / 1e9
+
+    def d2h():
+        h_out.copy_(dev, non_blocking=True)
+
+    def h2d():
+        dev.copy_(h_in, non_blocking=True)
+
+    def duplex():
+        h_out.copy_(dev, non_blocking=True)
+        with torch.cuda.stream(side):
+            dev2.copy_(h_in, non_blocking=True)
+    res = {"d2h_GBps_per_rank_all_ranks_busy": round(timed(d2h), 2), "h2d_GBps_per_rank_all_ranks_busy": round(timed(h2d), 2),
+           "duplex_GBps_each_way_per_rank": round(timed(duplex), 2), "block_MiB": block >> 20,
+           "how": "pinned host <-> HBM, cudaMemcpyAsync, every rank at the same time, slowest rank"}
+    del dev, dev2, h_out, h_in
+    return res
+
+
+def strong_scaling(ec, L, torch, dist, rank, world, local, barrier, max_over_ranks, peak, parity):
+    """BASELINE configs 4 and 5 as the north star states them: ONE 32768^2 raster in row strips over the N GPUs, the
+    reduction finishing across the GPUs; 8 NDVI tiles dealt over the N GPUs. Fixed total work (strong scaling): at N > 1
+    rank 0 also times the same work alone on its GPU in the same run (`n1_ms_same_run`), so the speed-up does not depend
+    on another run or another box. Every result is asserted: against constants the oracle computed over the whole
+    raster (tests/golden/bench_expected.json), against the oracle on sampled windows, and between the ranks."""
+    from erased_cells_b200 import CellBuffer, CellType, sharding, synth
+    from oracle import oracle as orc
+    res = {"n_gpus": world, "scaling": "strong"}
+    expected = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_expected.json")))
+
+    def timed(fn, iters, warm=3):
+        """device time per call (CUDA events on the launching stream, max over ranks) and host-visible wall clock per call"""
+        for _ in range(warm):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.current_stream().synchronize()
+        wall = (time.perf_counter() - t0) * 1e3 / iters
+        barrier()
+        return max_over_ranks(a.elapsed_time(b)) / iters, max_over_ranks(wall)
+
+    def solo(fn, iters, warm=3):
+        """rank 0 alone (the other ranks wait at the barriers): the N = 1 time of the same work in the same run"""
+        ms = 0.0
+        barrier()
+        if rank == 0:
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / iters
+        barrier()
+        return max_over_ranks(ms)
+
+    def entry(ms, wall_ms, nbytes, ncells, n1_ms=None, **kw):
+        g = nbytes / (ms * 1e-3) / 1e9
+        e = dict(ms=round(ms, 4), host_visible_ms=round(wall_ms, 4), GBps=round(g, 1), Gcells_s=round(ncells / (ms * 1e-3) / 1e9, 2),
+                 frac_of_measured_peak_x_gpus=round(g / (peak * world), 3), **kw)
+        if n1_ms is not None:
+            e.update(n1_ms_same_run=round(n1_ms, 4), speedup_vs_n1_same_run=round(n1_ms / ms, 3), linear_speedup=world)
+        return e
+
+    # ---- config 4: f32 32768^2 min_max (+ statistics), row strips, cross-GPU finish -----------------------------------
+    side = 32768
+    n4 = side * side
+    exp4 = expected["c4_f32_32768"]
+    off, ln = sharding.row_strip(side, side, world, rank)
+    strip = synth.device(CellType.Float32, ln, 0xEC40, index_offset=off, kind=synth.REAL_RANGE, lo=-1e4, hi=1e4)
+    keys = torch.empty(2, dtype=torch.int64, device="cuda")
+    hkeys = torch.empty(2, dtype=torch.int64).pin_memory()
+
+    def c4_nccl():
+        ec._lib.check(L.ec_buf_min_max_keys(strip._h, None, C.c_void_p(keys.data_ptr())))
+        if world > 1:
+            dist.all_reduce(keys, op=dist.ReduceOp.MIN)
+        hkeys.copy_(keys, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        mn, mx = ec._lib.Value(), ec._lib.Value()
+        ec._lib.check(L.ec_min_max_from_keys(int(CellType.Float32), hkeys.numpy().ctypes.data_as(C.POINTER(C.c_int64)), C.byref(mn), C.byref(mx)))
+        return hex(mn.bits), hex(mx.bits)
+
+    comm = sharding.Comm.create() if world > 1 else None
+
+    def c4_fused():
+        mn, mx = comm.min_max(strip) if comm is not None else strip.min_max()
+        return hex(mn.bits), hex(mx.bits)
+
+    n1_ms = None
+    if world > 1:
+        whole = [None]
+        if rank == 0:
+            whole[0] = synth.device(CellType.Float32, n4, 0xEC40, kind=synth.REAL_RANGE, lo=-1e4, hi=1e4)
+        n1_ms = solo(lambda: whole[0].min_max(), 10)
+        whole[0] = None
+    want = (exp4["min_bits"], exp4["max_bits"])
+    got_nccl, got_fused = c4_nccl(), c4_fused()
+    parity["c4_min_max_equals_oracle_constant"] = got_nccl == want and got_fused == want
+    # sampled windows of this rank's strip against the oracle (the strip really holds the raster the constant was computed from)
+    okw = True
+    for w0 in (0, (ln // 2) & ~127, ln - (1 << 16)):
+        mn, mx = strip.view(w0, 1 << 16).min_max()
+        omn, omx = orc.tight_min_max(synth.host(CellType.Float32, 1 << 16, 0xEC40, index_offset=off + w0, kind=synth.REAL_RANGE, lo=-1e4, hi=1e4))
+        okw &= (mn.bits, mx.bits) == (omn.bits, omx.bits)
+    parity["c4_sampled_windows_vs_oracle"] = okw
+    ms, wall = timed(c4_fused, 20)
+    res["c4_f32_32768_min_max"] = entry(ms, wall, 4.0 * n4, n4, n1_ms, shards=world, result_bits=list(got_fused), expected_bits=list(want),
+                                        finish=("ec_buf_min_max_sharded: reduction + NVLink peer exchange + fold in ONE kernel per GPU, result polled from mapped pinned memory"
+                                                if comm is not None and comm.peer_exchange else "ec_buf_min_max (one GPU)" if comm is None else "kernel + ncclAllReduce (ec_comm)"))
+    ms, wall = timed(c4_nccl, 20)
+    res["c4_f32_32768_min_max_nccl"] = entry(ms, wall, 4.0 * n4, n4, n1_ms, shards=world, result_bits=list(got_nccl),
+                                             finish="shard kernel + torch.distributed all-reduce(MIN, 2 x int64) + D2H of the result")
+    st = comm.statistics(strip) if comm is not None else strip.statistics()
+    parity["c4_statistics_count_min_max"] = (st.count, hex(st.min.bits), hex(st.max.bits)) == (exp4["count"], exp4["min_bits"], exp4["max_bits"])
+    n1s = None
+    if world > 1:
+        whole = [None]
+        if rank == 0:
+            whole[0] = synth.device(CellType.Float32, n4, 0xEC40, kind=synth.REAL_RANGE, lo=-1e4, hi=1e4)
+        n1s = solo(lambda: whole[0].statistics(), 5)
+        if rank == 0:
+            s1 = whole[0].statistics()
+            parity["c4_statistics_bits_equal_one_gpu"] = np.array_equal(np.array([s1.mean, s1.stddev]).view(np.uint64), np.array([st.mean, st.stddev]).view(np.uint64))
+        whole[0] = None
+    ms, wall = timed((lambda: comm.statistics(strip)) if comm is not None else (lambda: strip.statistics()), 5)
+    res["c4_f32_32768_statistics"] = entry(ms, wall, 4.0 * n4, n4, n1s, shards=world, result=[st.count, st.mean, st.stddev],
+                                           note="extension (the reference has no statistics): parity unpinned, bit-identical for every N by construction")
+    del strip
+    if comm is not None:
+        comm.close()
+
+    # ---- config 5: 8 NDVI tiles (u16 32768^2 each) over the N GPUs: fused (nir - red) / (nir + red) -> f64, per-tile min_max,
+    #      then ONE all-reduce for the mosaic's min / max ------------------------------------------------------------------
+    n5 = side * side
+    tiles = [t for t in range(8) if t % world == rank]
+
+    def make(t):
+        return (synth.device(CellType.UInt16, n5, 0xEC50 + t, kind=synth.INT_RANGE, lo=5000, hi=40000, period=1000, sentinel=0),
+                synth.device(CellType.UInt16, n5, 0xEC58 + t, kind=synth.INT_RANGE, lo=5000, hi=40000, period=1000, sentinel=0))
+    bands = {t: make(t) for t in tiles}
+    mosaic = torch.empty(2, dtype=torch.int64, device="cuda")
+
+    def c5(which):
+        k0 = k1 = None
+        for t in which:
+            nir, red = bands[t]
+            ndvi = nir.normalized_difference(red)
+            mn, mx = ndvi.min_max()
+            k = sharding.keys_of(mn, mx)
+            k0 = k[0] if k0 is None else min(k0, k[0])
+            k1 = k[1] if k1 is None else min(k1, k[1])
+        return k0, k1
+
+    def c5_step():
+        k0, k1 = c5(tiles)
+        if world > 1:
+            mosaic.copy_(torch.tensor([k0, k1], dtype=torch.int64))
+            dist.all_reduce(mosaic, op=dist.ReduceOp.MIN)
+            k0, k1 = [int(x) for x in mosaic.tolist()]
+        return k0, k1
+
+    # parity: sampled windows of every local tile's NDVI against the oracle
+    ok5 = True
+    for t in tiles:
+        nir, red = bands[t]
+        for w0 in (0, n5 - (1 << 16)):
+            got = nir.view(w0, 1 << 16).normalized_difference(red.view(w0, 1 << 16)).to_vec()
+            hn = synth.host(CellType.UInt16, 1 << 16, 0xEC50 + t, index_offset=w0, kind=synth.INT_RANGE, lo=5000, hi=40000, period=1000, sentinel=0)
+            hr = synth.host(CellType.UInt16, 1 << 16, 0xEC58 + t, index_offset=w0, kind=synth.INT_RANGE, lo=5000, hi=40000, period=1000, sentinel=0)
+            want5 = orc.tight_binary(orc.DIV, orc.tight_binary(orc.SUB, hn, hr), orc.tight_binary(orc.ADD, hn, hr))
+            ok5 &= bool(np.array_equal(got.view(np.uint64), want5.view(np.uint64)))
+    parity["c5_ndvi_sampled_windows_vs_oracle"] = ok5
+    keys5 = c5_step()
+    ms, wall = timed(c5_step, 3, 1)
+    n1_5 = None
+    if world > 1:
+        if rank == 0:
+            for t in range(8):
+                if t not in bands:
+                    bands[t] = make(t)
+        n1_5 = solo(lambda: c5(range(8)), 2, 1)
+        if rank == 0:
+            parity["c5_mosaic_min_max_equals_one_gpu"] = tuple(int(x) for x in c5(range(8))) == tuple(int(x) for x in keys5)
+    mnv, mxv = sharding.values_of(CellType.Float64, [keys5[0], keys5[1]])
+    res["c5_ndvi_8_tiles_u16_32768"] = entry(ms, wall, 8 * (12.0 + 8.0) * n5, 8 * n5, n1_5, tiles_per_gpu=len(tiles), result_bits=[hex(mnv.bits), hex(mxv.bits)],
+                                             note="per tile: fused NDVI (12 B/cell) + min_max of the f64 result (8 B/cell); one 16-byte all-reduce per step")
+    bands.clear()
+    ec._lib.check(L.ec_trim())
+
+    # ---- the same raster driven by ONE process over all N GPUs through the plain C ABI (tools/shard_latency.c) ---------
+    exe = os.path.join(ROOT, "tools", "bin", "shard_latency")
+    if world > 1 and os.path.exists(exe):
+        host_group = dist.new_group(backend="gloo")
+        barrier()
+        torch.cuda.empty_cache()
+        single = None
+        if rank == 0:
+            try:
+                env = dict(os.environ)
+                for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "EC_DEVICE", "EC_DEVICES"):
+                    env.pop(k, None)
+                r = subprocess.run([exe, str(side), ",".join(str(i) for i in range(world)), "30"], capture_output=True, text=True, timeout=300, env=env)
+                single = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1][len("RESULT "):])
+                parity["c4_single_process_sharded_equals_oracle_constant"] = all(
+                    [hex(int(b, 16)) for b in single[k]] == list(want) for k in single if k.startswith("bits_"))
+            except Exception as e:  # the probe is extra evidence, not the bench
+                single = {"error": repr(e)[:300]}
+        res["c4_single_process_all_gpus"] = single
+        # the other ranks must not touch their GPUs meanwhile: they wait on the host (gloo); an NCCL barrier would spin a kernel there
+        dist.barrier(group=host_group)
+        barrier()
+    return res
 
 
 def other_configs(ec, L, torch, dist, rank, world, barrier, max_over_ranks, peak):
@@ -504,7 +791,7 @@ def other_configs(ec, L, torch, dist, rank, world, barrier, max_over_ranks, peak
     ma, mb = MaskedCellBuffer.from_buffer_with_nodata(a, nd), MaskedCellBuffer.from_buffer_with_nodata(b, nd)
     c3["masked_sub_i16_i16"] = entry(timed(lambda: ma - mb), 12.375 * n3, n3)
     r = ma - mb
-    c3["masked_mul_scalar_f64"] = entry(timed(lambda: r * 0.0001), 16.0 * n3, n3, note="buffer kernel only; the mask is cloned (1/4 B/cell more)")
+    c3["masked_mul_scalar_f64"] = entry(timed(lambda: r * 0.0001), 16.0 * n3, n3, note="the result shares the operand's mask words (refcounted): 16 B/cell, no mask traffic")
     def c3_lazy():  # `(&ma - &mb) * 0.0001` through the operators, deferred: one fused data pass + the mask AND
         with ec.lazy():
             x = (ma - mb) * 0.0001
@@ -513,49 +800,14 @@ def other_configs(ec, L, torch, dist, rank, world, barrier, max_over_ranks, peak
     c3["masked_sub_then_scale_lazy_1_pass"] = entry(timed(c3_lazy), 12.0 * n3, n3, note="data kernel 12 B/cell; mask AND + clone ride along (5/8 B/cell)")
     rs = r * 0.0001
     c3["masked_min_max_f64"] = entry(timed(lambda: rs.min_max()), 8.125 * n3, n3, note="includes the 16-byte D2H + stream sync of the result")
-    c3["counts"] = entry(timed(lambda: rs.counts()), 0.125 * n3, n3)
+    c3["counts"] = entry(timed(lambda: rs.counts()), 0.125 * n3, n3, note="the kernel that produced the mask counted its set bits: no launch, the cached value")
+    fresh = ~(~rs.mask())
+    c3["counts_popcount_pass"] = entry(timed(lambda: (rs.mask() & fresh).counts()), 0.375 * n3, n3, note="mask AND (3/8 B/cell) with the count produced by the same kernel, polled from pinned memory")
     # statistics extension (count/min/max/mean/stddev; the reference has none): integer cells of <= 32 bits are ONE pass
     c3["statistics_masked_i16_one_pass"] = entry(timed(lambda: ma.statistics()), 2.125 * n3, n3, note="extension: min, max, count, sum x, sum x^2 in one read; host finish + sync included")
     c3["statistics_masked_f64_two_passes"] = entry(timed(lambda: rs.statistics()), 8.125 * n3, n3, note="extension: min_max pass + FP64 window moments pass; bytes counted once")
     res["c3_masked_i16_16384"] = c3
     del a, b, ma, mb, r, rs
-
-    # config 4: f32 32768^2 min_max, row strips over the ranks (strong scaling) + one NCCL all-reduce of 16 bytes
-    n4 = 32768 * 32768
-    off, ln = C.c_size_t(), C.c_size_t()
-    ec._lib.check(L.ec_row_strip(32768, 32768, world, rank, C.byref(off), C.byref(ln)))
-    strip = synth.device(CellType.Float32, ln.value, 0xEC40, index_offset=off.value, kind=synth.REAL_RANGE, lo=-1e4, hi=1e4)
-    keys = torch.empty(2, dtype=torch.int64, device="cuda")
-    hkeys = torch.empty(2, dtype=torch.int64).pin_memory()
-
-    def c4():
-        ec._lib.check(L.ec_buf_min_max_keys(strip._h, None, C.c_void_p(keys.data_ptr())))
-        if world > 1:
-            dist.all_reduce(keys, op=dist.ReduceOp.MIN)
-        hkeys.copy_(keys, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        mn, mx = ec._lib.Value(), ec._lib.Value()
-        ec._lib.check(L.ec_min_max_from_keys(int(CellType.Float32), hkeys.numpy().ctypes.data_as(C.POINTER(C.c_int64)), C.byref(mn), C.byref(mx)))
-        return mn.bits, mx.bits
-    ms4 = timed(c4, 10)
-    res["c4_f32_32768_min_max_sharded"] = entry(ms4, 4.0 * n4, n4, scaling="strong", shards=world, result_bits=[hex(x) for x in c4()],
-                                                note="shard kernel + torch.distributed all-reduce(MIN, 2 x int64) + D2H of the result, host-visible")
-    if world > 1:  # the same through the library's communicator: reduction + NVLink peer exchange + final fold in ONE kernel per GPU
-        from erased_cells_b200 import sharding
-        comm = sharding.Comm.create()
-        got = comm.min_max(strip)
-        res["c4_f32_32768_min_max_sharded_fused"] = entry(timed(lambda: comm.min_max(strip), 10), 4.0 * n4, n4, scaling="strong", shards=world,
-                                                          peer_exchange=comm.peer_exchange, result_bits=[hex(got[0].bits), hex(got[1].bits)],
-                                                          note="ec_buf_min_max_sharded: one kernel per GPU when peer_exchange is true, else kernel + NCCL")
-        st = comm.statistics(strip)
-        res["c4_f32_32768_statistics_sharded"] = entry(timed(lambda: comm.statistics(strip), 5), 4.0 * n4, n4, scaling="strong", shards=world,
-                                                       result=[st.count, st.mean, st.stddev], note="extension, ec_buf_statistics_sharded: fused sharded min_max, FP64 moments pass per strip, one all-reduce of 136 B, host finish")
-        comm.close()
-    else:
-        st = strip.statistics()
-        res["c4_f32_32768_statistics"] = entry(timed(lambda: strip.statistics(), 5), 4.0 * n4, n4, result=[st.count, st.mean, st.stddev],
-                                               note="extension: min_max pass + FP64 window moments pass (FP64-issue-bound for f32); bytes counted once")
-    del strip
 
     # config 5: NDVI (nir - red) / (nir + red), u16 32768^2 -> f64, one tile per GPU (weak)
     n5 = 32768 * 32768

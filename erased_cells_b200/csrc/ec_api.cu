@@ -13,7 +13,9 @@
 #include <limits>
 #include <map>
 #include <memory>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "ec_internal.hpp"
