@@ -249,6 +249,7 @@ def run_ours(args, out):
     ec._lib.check(L.ec_set_stream(C.c_void_p(stream.cuda_stream)))
     assert L.ec_get_stream() == stream.cuda_stream
     bind_to_gpu_numa_node(local)
+    L.ec_set_min_max_cache(0)  # every timed min_max below reads its raster from HBM (a buffer would otherwise remember the result)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version/debug lines go to stderr: stdout is the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -644,7 +645,16 @@ def strong_scaling(ec, L, torch, dist, rank, world, local, barrier, max_over_ran
         whole[0] = None
     ms, wall = timed((lambda: comm.statistics(strip)) if comm is not None else (lambda: strip.statistics()), 5)
     res["c4_f32_32768_statistics"] = entry(ms, wall, 4.0 * n4, n4, n1s, shards=world, result=[st.count, st.mean, st.stddev],
-                                           note="extension (the reference has no statistics): parity unpinned, bit-identical for every N by construction")
+                                           note="extension (the reference has no statistics): parity unpinned, bit-identical for every N by construction; "
+                                                "min_max pass + one pass of exact integer sums over the cells quantised to 2^-26 of their range; bytes counted once")
+    if comm is None:  # when the raster's min_max is already known (ec_buf_min_max ran before, the buffer remembers it): ONE pass
+        L.ec_set_min_max_cache(1)
+        strip.min_max()
+        s1 = strip.statistics()
+        parity["c4_statistics_one_pass_equals_two_pass"] = np.array_equal(np.array([s1.mean, s1.stddev]).view(np.uint64), np.array([st.mean, st.stddev]).view(np.uint64))
+        ms, wall = timed(lambda: strip.statistics(), 5)
+        L.ec_set_min_max_cache(0)
+        res["c4_f32_32768_statistics_min_max_known"] = entry(ms, wall, 4.0 * n4, n4, None, shards=world, note="one pass: the buffer remembers its min_max from an earlier call")
     del strip
     if comm is not None:
         comm.close()

@@ -90,6 +90,7 @@ def _signatures():
         "ec_device_count": (I, []),
         "ec_set_shard_min_cells": (SZ, [SZ]),
         "ec_set_shard_finish": (I, [I]),
+        "ec_set_min_max_cache": (I, [I]),
         "ec_buf_shard_count": (I, [VP]),
         "ec_mask_shard_count": (I, [VP]),
         "ec_buf_shard": (S, [VP, I, C.POINTER(ShardInfo), PVP]),

@@ -978,6 +978,17 @@ ec_status int_stats_begin(const ec_buf* b, const ec_mask* m, StatsPending* p) {
     EC_CUDA_TRY(cudaMemcpyAsync(p->pin, acc.p, sizeof kIntStatsInit, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
     return EC_OK;
 }
+ec_status quant_stats_begin(const ec_buf* b, const ec_mask* m, int exp2, StatsPending* p) {
+    EC_TRY(ensure());
+    EC_TRY(resolve(b));
+    EC_TRY(stats_pending(p, 8));
+    Scratch acc;
+    EC_TRY(acc.alloc(sizeof kIntStatsInit));
+    EC_CUDA_TRY(cudaMemcpyAsync(acc.p, kIntStatsInit, sizeof kIntStatsInit, cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
+    EC_LAUNCH(launch_quant_stats(launch_ctx(), rd(b), m ? rdm(m) : nullptr, b->len, static_cast<unsigned long long*>(acc.p), exp2), "quant_stats");
+    EC_CUDA_TRY(cudaMemcpyAsync(p->pin, acc.p, sizeof kIntStatsInit, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
+    return EC_OK;
+}
 ec_status moments_begin(const ec_buf* b, const ec_mask* m, double pivot, int exp2, StatsPending* p) {
     EC_TRY(ensure());
     EC_TRY(resolve(b));
@@ -1480,6 +1491,8 @@ ec_status ec_buf_view(const ec_buf* b, size_t offset_cells, size_t len, ec_buf**
     v->ct = b->ct; v->owned = b->owned; v->len = len; v->capacity_bytes = len * kSize[b->ct]; v->dev = b->dev;
     v->dptr = static_cast<char*>(b->dptr) + offset_cells * kSize[b->ct];
     v->blk = b->blk;
+    if (v->blk) { v->blk->views.fetch_add(1); v->is_view = true; }
+    const_cast<ec_buf*>(b)->mm_known = false;  // the cells can now change behind b's back
     if (b->ready) cudaStreamWaitEvent(device_stream(b->dev), b->ready, 0);  // the view has no event of its own: order it after the upload now
     *out = v;
     return EC_OK;
@@ -1500,6 +1513,7 @@ ec_status ec_buf_clone(const ec_buf* b, ec_buf** out) {
 void ec_buf_free(ec_buf* b) {
     if (!b) return;
     for (ec_buf* part : b->parts) ec_buf_free(part);
+    if (b->is_view && b->blk) b->blk->views.fetch_sub(1);
     if (b->ready) {
         cudaEventSynchronize(b->ready);
         cudaEventDestroy(b->ready);
@@ -1541,6 +1555,7 @@ ec_status ec_buf_put(ec_buf* b, size_t index, const ec_value* value) {
     if (!ct_ok(value->ct)) return invalid("cell type");
     if (!ct_fits(value->ct, b->ct)) return narrowing(value->ct, b->ct);  // convert()? happens before the index (src/buffer.rs:137)
     if (index >= b->len) { set_error("index out of bounds: the len is %zu but the index is %zu", b->len, index); return EC_OOB; }
+    b->mm_known = false;
     if (is_sharded(b)) { const int g = sh_part_of(b->offs, index); DevScope on(g); return ec_buf_put(b->parts[g], index - b->offs[g], value); }
     DevScope on(b->dev);
     const ec_value c = value_widen(*value, b->ct);
@@ -1557,6 +1572,7 @@ ec_status ec_buf_extend_host(ec_buf* b, uint8_t ct, const void* host, size_t n) 
     if (!ct_ok(ct)) return invalid("cell type");
     if (!b->owned) return invalid("cannot extend a wrapped buffer");
     if (n == 0) return EC_OK;
+    b->mm_known = false;
     if (is_sharded(b)) {  // the appended cells join the last strip
         const int g = static_cast<int>(b->parts.size()) - 1;
         DevScope on(g);
@@ -1687,19 +1703,36 @@ ec_status ec_buf_convert(const ec_buf* b, uint8_t ct, ec_buf** out) {
     *out = o;
     return EC_OK;
 }
+static bool g_mm_cache = env_int("EC_MIN_MAX_CACHE", 1) != 0;
+static bool mm_cacheable(const ec_buf* b) {  // nothing is remembered about cells another handle can change
+    if (!g_mm_cache) return false;
+    if (b->blk && b->blk->views.load() != 0) return false;
+    for (const ec_buf* part : b->parts)
+        if (!mm_cacheable(part)) return false;
+    return b->owned;
+}
+int ec_set_min_max_cache(int on) { const int prev = g_mm_cache; g_mm_cache = on != 0; return prev; }
 static ec_value key_value(uint8_t ct, uint64_t key) { return tagged<uint64_t>(ct, key_to_bits(ct, key)); }
 ec_status ec_buf_min_max(const ec_buf* b, const ec_mask* m, ec_value* mn, ec_value* mx) {
     EC_TRY(ensure());
     if (m && m->len != b->len) { set_error("Mask and buffer must have the same length."); return EC_LEN_MISMATCH; }
     uint64_t k[2];
     key_seeds(b->ct, &k[0], &k[1]);
-    if (is_sharded(b) || (m && is_sharded(m))) {
+    const bool cacheable = !m && mm_cacheable(b);
+    if (cacheable && b->mm_known) {
+        k[0] = b->mm_k0; k[1] = b->mm_k1;
+    } else if (is_sharded(b) || (m && is_sharded(m))) {
         EC_TRY(sh_min_max(b, m, &k[0], &k[1]));
     } else if (b->len) {
         DevScope on(b->dev);
         PendingReduce pend;
         EC_TRY(min_max_begin(b, m, nullptr, &pend, nullptr));
         EC_TRY(reduce_end(pend, &k[0], &k[1]));
+    }
+    if (cacheable && !b->mm_known) {  // a cache: concurrent readers store the same values
+        ec_buf* w = const_cast<ec_buf*>(b);
+        w->mm_k0 = k[0]; w->mm_k1 = k[1];
+        __atomic_store_n(&w->mm_known, true, __ATOMIC_RELEASE);
     }
     *mn = key_value(b->ct, k[0]);
     *mx = key_value(b->ct, k[1]);
@@ -1713,6 +1746,14 @@ ec_status ec_statistics_plan(const ec_value* mn, const ec_value* mx, int* kind, 
     if (value_cmp(*mn, *mx) > 0) { *kind = EC_STATS_EMPTY; return EC_OK; }  // the (T::MAX, T::MIN) seeds survived
     const double lo = value_as_f64(*mn), hi = value_as_f64(*mx);
     if (!std::isfinite(lo) || !std::isfinite(hi)) { *kind = EC_STATS_NONFINITE; return EC_OK; }
+    if (mn->ct == EC_FLOAT32) {  // quantised route: no pivot on the device, exp2 = E with every |cell| < 2^E
+        const double top = std::fabs(lo) > std::fabs(hi) ? std::fabs(lo) : std::fabs(hi);
+        int e = 0;
+        if (top != 0) (void)std::frexp(top, &e);
+        *kind = EC_STATS_REGULAR;
+        *exp2 = e;
+        return EC_OK;
+    }
     const volatile double half_lo = lo * 0.5, half_hi = hi * 0.5;  // one rounding per step, as the oracle states it
     const double p = half_lo + half_hi;
     const double up = hi - p, down = p - lo;
@@ -1736,8 +1777,9 @@ ec_status ec_buf_moments(const ec_buf* b, const ec_mask* m, double pivot, int ex
     DevScope on(b->dev);
     StatsPending pend;
     uint64_t w[EC_MOMENT_WORDS];
-    if (stats_integer_route(b->ct)) {
-        EC_TRY(int_stats_begin(b, m, &pend));
+    if (stats_integer_route(b->ct) || b->ct == EC_FLOAT32) {
+        if (b->ct == EC_FLOAT32) EC_TRY(quant_stats_begin(b, m, exp2, &pend));
+        else EC_TRY(int_stats_begin(b, m, &pend));
         EC_TRY(stats_end(pend, w));
         memcpy(raw, w, 5 * sizeof(uint64_t));
         return EC_OK;
@@ -1765,6 +1807,18 @@ ec_status ec_statistics_finish(const uint64_t* raws, size_t n_parts, const ec_va
     if (kind == EC_STATS_NONFINITE) {
         const double lo = value_as_f64(*mn), hi = value_as_f64(*mx);
         if (!std::isnan(lo) && !std::isnan(hi) && !(std::isinf(lo) && std::isinf(hi))) out->mean = std::isinf(lo) ? lo : hi;
+        return EC_OK;
+    }
+    if (mn->ct == EC_FLOAT32) {
+        // quantised route: the sums are those of the int32 raster q = rint(x * 2^k), k = 26 - E. Finish that integer
+        // raster (min / max quantise monotonically) and scale the result back by 2^-k (exact).
+        const int k = 26 - e;
+        const ec_value qmn = tagged<int32_t>(EC_INT32, static_cast<int32_t>(std::nearbyint(std::ldexp(value_as_f64(*mn), k))));
+        const ec_value qmx = tagged<int32_t>(EC_INT32, static_cast<int32_t>(std::nearbyint(std::ldexp(value_as_f64(*mx), k))));
+        ec_statistics q;
+        EC_TRY(ec_statistics_finish(raws, n_parts, &qmn, &qmx, &q));
+        out->mean = std::ldexp(q.mean, -k);
+        out->stddev = std::ldexp(q.stddev, -k);
         return EC_OK;
     }
     // one rounding per operation (host code is built with -ffp-contract=off; int128 -> double is round-to-nearest-even)

@@ -26,6 +26,7 @@ struct DevBlock {
     int dev;
     cudaStream_t home;
     std::atomic<int> snapshots{0};       // pending lazy expressions that read this block: in-place mutation copies first
+    std::atomic<int> views{0};           // live views of the block: a put through one is seen by all, so nothing about the cells is cached meanwhile
     std::vector<std::pair<cudaStream_t, int>> foreign;  // other (stream, logical device) that touched the block (guarded by the allocator mutex)
     DevBlock(void* q, int d, cudaStream_t s) : p(q), dev(d), home(s) {}
     DevBlock(const DevBlock&) = delete;
@@ -48,6 +49,11 @@ struct ec_buf {
     int dev = 0;
     std::vector<ec_buf*> parts;
     std::vector<size_t> offs;
+    // min_max of all cells (order keys), remembered once any unmasked min_max has run and dropped by put / extend: a later
+    // min_max is free, and statistics of Float32 / 64-bit cells need no min_max pass of their own
+    bool mm_known = false;
+    uint64_t mm_k0 = 0, mm_k1 = 0;
+    bool is_view = false;
 };
 // Validity bits, packed; plain or sharded like ec_buf. The words are refcounted (a clone shares them until one side is
 // mutated). The number of set bits is cached: kernels that produce a mask count as they go and the last CTA
@@ -116,6 +122,7 @@ ec_status popcount_begin(const ec_mask* m, const PeerExchange* px, uint64_t seco
 ec_status first_diff_begin(const ec_buf* l, const ec_buf* r, size_t n, PendingReduce* pend);
 ec_status mask_first_diff(const ec_mask* l, const ec_mask* r, size_t n, uint64_t* bit_out);
 ec_status int_stats_begin(const ec_buf* b, const ec_mask* m, StatsPending* p);
+ec_status quant_stats_begin(const ec_buf* b, const ec_mask* m, int exp2, StatsPending* p);
 ec_status moments_begin(const ec_buf* b, const ec_mask* m, double pivot, int exp2, StatsPending* p);
 ec_status stats_end(const StatsPending& p, uint64_t* w);
 bool stats_integer_route(uint8_t ct);
@@ -233,6 +240,8 @@ ec_status reduce_popcount_peer(const ec_mask* m, const PeerExchange& px, uint64_
 cudaError_t launch_moments(const Launch& L, int ct, const void* a, const uint32_t* mask, size_t n, double pivot, double scale,
                            unsigned long long* acc);
 cudaError_t launch_int_stats(const Launch& L, int ct, const void* a, const uint32_t* mask, size_t n, unsigned long long* acc);
+// Float32 cells below 2^exp2 in magnitude, read as the int32 raster rint(x * 2^(26 - exp2)): same accumulators as launch_int_stats
+cudaError_t launch_quant_stats(const Launch& L, const void* a, const uint32_t* mask, size_t n, unsigned long long* acc, int exp2);
 cudaError_t launch_first_diff(const Launch& L, int cell_bytes, const void* a, const void* b, size_t n,
                               const ReduceScratch& s);
 // masks

@@ -107,8 +107,9 @@ __global__ void __launch_bounds__(THREADS) map1_kernel(const typename F::A* __re
 }
 
 // ---- two-input map, optionally carrying the validity mask (packed words) along ---------------------
-// When lm != nullptr the CTA that owns a tile also ANDs the tile's mask words (32 cells per word):
-// MaskedCellBuffer op (src/masked/masked_buffer.rs:326-336) in one launch.
+// The MASKED flavour also ANDs the tile's mask words (32 cells per word) in the CTA that owns the tile and counts the
+// set bits it wrote: MaskedCellBuffer op (src/masked/masked_buffer.rs:326-336) plus Mask::counts of the result in one
+// launch. It is a separate instantiation so that the unmasked kernels (issue-limited for the division) carry none of it.
 // Register budget: with narrow operands (<= 8 input bytes per cell) the loads in flight are small, so the
 // kernel is held to 64 registers (>= 1024 resident threads per SM) — the f64 division path otherwise drifts
 // to 66 registers = 3 CTAs/SM in the fused functors (ncu, profiles/). Wide operands keep UNROLL x 32 bytes
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(THREADS) map1_kernel(const typename F::A* __re
 template <class F> constexpr int map2_min_ctas(int threads) {
     return (sizeof(typename F::A) + sizeof(typename F::B) <= 8 ? 1024 : 512) / threads;
 }
-template <class F, int VB, int UNROLL, int THREADS>
+template <class F, int VB, int UNROLL, int THREADS, bool MASKED = false>
 __global__ void __launch_bounds__(THREADS, map2_min_ctas<F>(THREADS)) map2_kernel(const typename F::A* __restrict__ a,
                                                        const typename F::B* __restrict__ b,
                                                        typename F::O* __restrict__ o, size_t n, F f,
@@ -141,10 +142,12 @@ __global__ void __launch_bounds__(THREADS, map2_min_ctas<F>(THREADS)) map2_kerne
             vb[u] = ld_stream<B, V>(b + base + size_t(u) * THREADS * V);
         }
         uint4 wl, wr;
-        const bool mask_lane = lm != nullptr && threadIdx.x < TILE_WORDS / 4;
-        if (mask_lane) {
-            wl = *reinterpret_cast<const uint4*>(lm + t * TILE_WORDS + threadIdx.x * 4);
-            wr = *reinterpret_cast<const uint4*>(rm + t * TILE_WORDS + threadIdx.x * 4);
+        const bool mask_lane = MASKED && threadIdx.x < TILE_WORDS / 4;
+        if constexpr (MASKED) {
+            if (mask_lane) {
+                wl = *reinterpret_cast<const uint4*>(lm + t * TILE_WORDS + threadIdx.x * 4);
+                wr = *reinterpret_cast<const uint4*>(rm + t * TILE_WORDS + threadIdx.x * 4);
+            }
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
@@ -153,15 +156,17 @@ __global__ void __launch_bounds__(THREADS, map2_min_ctas<F>(THREADS)) map2_kerne
             for (int j = 0; j < V; ++j) vo.v[j] = f(va[u].v[j], vb[u].v[j]);
             st_stream<O, V>(o + base + size_t(u) * THREADS * V, vo);
         }
-        if (mask_lane) {
-            const uint4 w = make_uint4(wl.x & wr.x, wl.y & wr.y, wl.z & wr.z, wl.w & wr.w);
-            *reinterpret_cast<uint4*>(om + t * TILE_WORDS + threadIdx.x * 4) = w;
-            ones += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+        if constexpr (MASKED) {
+            if (mask_lane) {
+                const uint4 w = make_uint4(wl.x & wr.x, wl.y & wr.y, wl.z & wr.z, wl.w & wr.w);
+                *reinterpret_cast<uint4*>(om + t * TILE_WORDS + threadIdx.x * 4) = w;
+                ones += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+            }
         }
     }
     if (blockIdx.x == full % gridDim.x) {
         for (size_t i = full * TILE + threadIdx.x; i < n; i += THREADS) o[i] = f(a[i], b[i]);
-        if (lm != nullptr) {
+        if constexpr (MASKED) {
             const size_t words = (n + 31) / 32;
             for (size_t w = full * TILE_WORDS + threadIdx.x; w < words; w += THREADS) {
                 const uint32_t x = lm[w] & rm[w];
@@ -170,9 +175,11 @@ __global__ void __launch_bounds__(THREADS, map2_min_ctas<F>(THREADS)) map2_kerne
             }
         }
     }
-    if (lm != nullptr && mc.acc != nullptr) {  // uniform over the grid: Mask::counts of the result comes for free
-        const unsigned long long c = block_count(ones);
-        if (threadIdx.x == 0) publish_count(mc, c);
+    if constexpr (MASKED) {
+        if (mc.acc != nullptr) {  // uniform over the grid: Mask::counts of the result comes for free
+            const unsigned long long c = block_count<THREADS>(ones);
+            if (threadIdx.x == 0) publish_count(mc, c);
+        }
     }
 }
 

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(THREADS) mask_build_kernel(const U* __restrict
         }
     }
     if (mc.acc != nullptr) {
-        const unsigned long long c = block_count(ones);
+        const unsigned long long c = block_count<THREADS>(ones);
         if (threadIdx.x == 0) publish_count(mc, c);
     }
 }
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(THREADS) mask_bitop_kernel(int mop, const uint
         ones += __popc(x);
     }
     if (mc.acc != nullptr) {
-        const unsigned long long c = block_count(ones);
+        const unsigned long long c = block_count<THREADS>(ones);
         if (threadIdx.x == 0) publish_count(mc, c);
     }
 }

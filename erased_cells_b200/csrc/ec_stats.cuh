@@ -9,9 +9,9 @@
 //   mantissa bits, the remainder r = v - (t1 - 48) is exact, t2 = fl(r + 48 * 2^-48) carries rint(r * 2^95) — and
 //   the four integer streams are summed EXACTLY (128-bit two's complement).
 //
-// One streaming pass, algorithmic bytes per cell = size_of(T) (+ 1/8 with a mask); 12 FP64 operations per cell, which
-// is what bounds Float32 (64-bit cells stay HBM-bound). Integer cells of at most 32 bits never come here: for them
-// y is exact and the sums are exact integers, see int_stats_kernel below.
+// One streaming pass, algorithmic bytes per cell = size_of(T) (+ 1/8 with a mask); 12 FP64 operations per cell, hidden
+// behind the HBM traffic of 64-bit cells (UInt64, Int64, Float64 — the only types that come here). Integer cells of at
+// most 32 bits and Float32 cells take int_stats_kernel below: exact integer sums, no FP64.
 #pragma once
 #include "ec_reduce.cuh"
 
@@ -158,10 +158,19 @@ __global__ void __launch_bounds__(THREADS) moments_kernel(const T* __restrict__ 
 // the narrow types (as min_max_kernel does); a masked-out cell is forced to zero / to the identity of min and max.
 // acc[7] = {count, A.lo, A.hi, B.lo, B.hi, min (biased, preset to all ones), max (biased, preset to 0)};
 // A and B are 128-bit two's complement, summed across CTAs with carry-tracking atomics.
-template <class T, bool MASKED, int VB, int UNROLL, int THREADS>
+//
+// QUANT: Float32 cells take the same route. A f32 raster whose valid cells are all below 2^E in magnitude is read as
+// the int32 raster q = rint(x * 2^(26 - E)) (|q| <= 2^26, round half to even): cells within 2^3 of the largest
+// magnitude are exact on that grid (their own ulp is coarser), smaller ones are rounded by at most 2^-27 of the
+// largest magnitude — an eighth of the ulp the large cells carry. min, max, count, sum q and sum q^2 are then exact
+// integers like for any int32 raster, and the host turns them into mean / stddev and scales by 2^(E - 26). Two FP32
+// multiplies (the scale is split so that neither factor leaves the f32 range) and one cvt.rni per cell replace the
+// twelve FP64 operations of the window route, which is what kept Float32 statistics off the HBM roofline.
+template <class T, bool MASKED, int VB, int UNROLL, int THREADS, bool QUANT = false>
 __global__ void __launch_bounds__(THREADS) int_stats_kernel(const T* __restrict__ a, const uint32_t* __restrict__ m, size_t n,
-                                                            unsigned long long* __restrict__ acc) {
+                                                            unsigned long long* __restrict__ acc, float qs1 = 1.0f, float qs2 = 1.0f) {
     static_assert(sizeof(T) <= 4 && std::is_integral<T>::value, "integer cells of at most 32 bits");
+    static_assert(!QUANT || std::is_same<T, int32_t>::value, "quantised Float32 cells are read as int32");
     constexpr bool SG = std::is_signed<T>::value;
     constexpr int V = VB / sizeof(T);
     constexpr int W = VB / 4;
@@ -194,6 +203,7 @@ __global__ void __launch_bounds__(THREADS) int_stats_kernel(const T* __restrict_
 #pragma unroll
             for (int j = 0; j < W; ++j) {
                 uint32_t x = w[u].v[j];
+                if constexpr (QUANT) x = static_cast<uint32_t>(__float2int_rn(__fmul_rn(__fmul_rn(__uint_as_float(x), qs1), qs2)));
                 uint32_t kmin = x ^ BIAS, kmax = x ^ BIAS;
                 if constexpr (MASKED) {
                     [[maybe_unused]] const uint32_t b = (mw[u] >> (CPW * j)) & ((1u << CPW) - 1u);
@@ -266,8 +276,10 @@ __global__ void __launch_bounds__(THREADS) int_stats_kernel(const T* __restrict_
             bool valid = true;
             if constexpr (MASKED) valid = (m[i / 32] >> (i % 32)) & 1u;
             if (!valid) continue;
-            const int64_t x = static_cast<int64_t>(a[i]);
-            const uint32_t k = static_cast<uint32_t>(static_cast<bits_t<T>>(a[i])) ^ LB;
+            T cell = a[i];
+            if constexpr (QUANT) cell = static_cast<T>(__float2int_rn(__fmul_rn(__fmul_rn(__int_as_float(static_cast<int>(cell)), qs1), qs2)));
+            const int64_t x = static_cast<int64_t>(cell);
+            const uint32_t k = static_cast<uint32_t>(static_cast<bits_t<T>>(cell)) ^ LB;
             lo = min(lo, k);
             hi = max(hi, k);
             sum += x;

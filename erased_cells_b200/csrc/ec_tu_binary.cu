@@ -17,18 +17,35 @@ namespace ec {
 
 using LT = type_of<EC_LCT>::type;
 
-template <class F>
+// Loads in flight per operand. 4 everywhere, except where ptxas cannot fit the schedule into the 64 registers of the
+// 4-CTAs-per-SM budget: the division of 8-bit by 16-bit cells spills at 4 and not at 8 (ptxas -v), and the spill-free
+// form measured 11-14 % faster at 2^24 .. 2^28 cells (tools/map2_variants.cu, profiles/r02_map2_variants.txt).
+template <class F> struct map2_unroll { static constexpr int value = EC_UNROLL; };
+template <class L, class R> struct map2_unroll<BinaryF<L, R, OP_DIV>> {
+    static constexpr int value = (sizeof(L) == 1 && sizeof(R) == 2 && !is_fp<L> && !is_fp<R>) ? 8 : EC_UNROLL;
+};
+template <class F, bool MASKED = false>
 static cudaError_t go2(const Launch& Lc, const typename F::A* l, const typename F::B* r, double* out, size_t n, F f,
                        const uint32_t* lm, const uint32_t* rm, uint32_t* om, const MaskCount& mc) {
     constexpr int V = EC_VB / cmax<cmax<sizeof(typename F::A), sizeof(typename F::B)>(), sizeof(double)>();
-    constexpr size_t TILE = size_t(kThreads) * V * EC_UNROLL;
-    return launch_k(Lc, map2_kernel<F, EC_VB, EC_UNROLL, kThreads>, grid_for(n, TILE, Lc), kThreads, l, r, out, n, f, lm, rm, om, mc);
+    constexpr int U = MASKED ? EC_UNROLL : map2_unroll<F>::value;
+    constexpr size_t TILE = size_t(kThreads) * V * U;
+    return launch_k(Lc, map2_kernel<F, EC_VB, U, kThreads, MASKED>, grid_for(n, TILE, Lc), kThreads, l, r, out, n, f, lm, rm, om, mc);
 }
 static const MaskCount kNoCount{nullptr, nullptr, 0};
 
 template <class R>
 static cudaError_t binary_r(const Launch& Lc, int op, const LT* l, const R* r, double* out, size_t n,
                             const uint32_t* lm, const uint32_t* rm, uint32_t* om, const MaskCount& mc) {
+    if (lm != nullptr) {  // MaskedCellBuffer op: the flavour that carries the mask AND and its count along
+        switch (op) {
+            case OP_ADD: return go2<BinaryF<LT, R, OP_ADD>, true>(Lc, l, r, out, n, {}, lm, rm, om, mc);
+            case OP_SUB: return go2<BinaryF<LT, R, OP_SUB>, true>(Lc, l, r, out, n, {}, lm, rm, om, mc);
+            case OP_MUL: return go2<BinaryF<LT, R, OP_MUL>, true>(Lc, l, r, out, n, {}, lm, rm, om, mc);
+            case OP_DIV: return go2<BinaryF<LT, R, OP_DIV>, true>(Lc, l, r, out, n, {}, lm, rm, om, mc);
+        }
+        return cudaErrorInvalidValue;
+    }
     switch (op) {
         case OP_ADD: return go2(Lc, l, r, out, n, BinaryF<LT, R, OP_ADD>{}, lm, rm, om, mc);
         case OP_SUB: return go2(Lc, l, r, out, n, BinaryF<LT, R, OP_SUB>{}, lm, rm, om, mc);

@@ -3,6 +3,8 @@
 #include "ec_internal.hpp"
 #include "ec_stats.cuh"
 
+#include <cmath>
+
 #ifndef EC_VB
 #define EC_VB 32
 #endif
@@ -47,7 +49,6 @@ cudaError_t launch_moments(const Launch& Lc, int ct, const void* a, const uint32
     switch (ct) {  // 64-bit integers and floats; narrower integers take the exact integer route (launch_int_stats)
         case EC_UINT64: return moments_t<uint64_t>(Lc, a, mask, n, pivot, scale, acc);
         case EC_INT64: return moments_t<int64_t>(Lc, a, mask, n, pivot, scale, acc);
-        case EC_FLOAT32: return moments_t<float>(Lc, a, mask, n, pivot, scale, acc);
         case EC_FLOAT64: return moments_t<double>(Lc, a, mask, n, pivot, scale, acc);
     }
     return cudaErrorInvalidValue;
@@ -69,9 +70,31 @@ static cudaError_t int_stats_t(const Launch& Lc, const void* a, const uint32_t* 
     if (cap < (n >> 28) + 1) cap = (n >> 28) + 1;
     if (grid > cap) grid = cap;
     if (grid == 0) grid = 1;
-    if (mask) masked<<<int(grid), kStatThreads, 0, Lc.stream>>>(static_cast<const T*>(a), mask, n, acc);
-    else plain<<<int(grid), kStatThreads, 0, Lc.stream>>>(static_cast<const T*>(a), nullptr, n, acc);
+    if (mask) masked<<<int(grid), kStatThreads, 0, Lc.stream>>>(static_cast<const T*>(a), mask, n, acc, 1.0f, 1.0f);
+    else plain<<<int(grid), kStatThreads, 0, Lc.stream>>>(static_cast<const T*>(a), nullptr, n, acc, 1.0f, 1.0f);
     return cudaGetLastError();
+}
+// Float32 cells quantised to q = rint(x * qs1 * qs2) and summed as int32 (see int_stats_kernel)
+static cudaError_t quant_stats(const Launch& Lc, const void* a, const uint32_t* mask, size_t n, unsigned long long* acc, float qs1, float qs2) {
+    constexpr int V = EC_VB / 4;
+    constexpr size_t TILE = size_t(kStatThreads) * V * kIntStatUnroll;
+    auto masked = int_stats_kernel<int32_t, true, EC_VB, kIntStatUnroll, kStatThreads, true>;
+    auto plain = int_stats_kernel<int32_t, false, EC_VB, kIntStatUnroll, kStatThreads, true>;
+    static const size_t cap_masked = resident_ctas(masked, Lc), cap_plain = resident_ctas(plain, Lc);
+    size_t grid = n / TILE;
+    size_t cap = mask ? cap_masked : cap_plain;
+    if (cap < (n >> 28) + 1) cap = (n >> 28) + 1;
+    if (grid > cap) grid = cap;
+    if (grid == 0) grid = 1;
+    if (mask) masked<<<int(grid), kStatThreads, 0, Lc.stream>>>(static_cast<const int32_t*>(a), mask, n, acc, qs1, qs2);
+    else plain<<<int(grid), kStatThreads, 0, Lc.stream>>>(static_cast<const int32_t*>(a), nullptr, n, acc, qs1, qs2);
+    return cudaGetLastError();
+}
+cudaError_t launch_quant_stats(const Launch& Lc, const void* a, const uint32_t* mask, size_t n, unsigned long long* acc, int exp2) {
+    // 2^(26 - E) as two f32 factors, each a normal power of two; x * qs1 stays below 2^26 (no overflow), and whatever
+    // underflows on the way is far below one half and rounds to 0 either way
+    const int k = 26 - exp2, k1 = k > 120 ? 120 : k;
+    return quant_stats(Lc, a, mask, n, acc, std::ldexp(1.0f, k1), std::ldexp(1.0f, k - k1));
 }
 cudaError_t launch_int_stats(const Launch& Lc, int ct, const void* a, const uint32_t* mask, size_t n, unsigned long long* acc) {
     switch (ct) {

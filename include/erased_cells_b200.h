@@ -222,6 +222,10 @@ ec_status ec_buf_cmp(const ec_buf* l, const ec_buf* r, int* ordering);
  * are what a row-strip sharded caller composes: global min/max -> plan (host) -> per-strip moments (device, exact
  * integer sums) -> finish over all strips' raw words (host). */
 ec_status ec_buf_statistics(const ec_buf* b, const ec_mask* mask_or_null, ec_statistics* out);
+/* A buffer remembers the result of an unmasked ec_buf_min_max (put / extend forget it): a second min_max is free and
+ * ec_buf_statistics of Float32 / 64-bit cells skips its min_max pass. $EC_MIN_MAX_CACHE=0 / ec_set_min_max_cache(0)
+ * turn that off (benchmarks that want every call to touch HBM). Returns the previous setting. */
+int ec_set_min_max_cache(int on);
 ec_status ec_statistics_plan(const ec_value* min, const ec_value* max, int* kind, double* pivot, int* exp2);
 ec_status ec_buf_moments(const ec_buf* b, const ec_mask* mask_or_null, double pivot, int exp2, uint64_t raw[EC_MOMENT_WORDS]);
 ec_status ec_statistics_finish(const uint64_t* raws, size_t n_parts, const ec_value* min, const ec_value* max,

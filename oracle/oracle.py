@@ -442,6 +442,9 @@ def statistics_plan(mn: Value, mx: Value):
     lo, hi = np.float64(_value_f64(mn)), np.float64(_value_f64(mx))
     if not (np.isfinite(lo) and np.isfinite(hi)):
         return ST_NONFINITE, 0.0, 0
+    if mn.ct == Float32:  # quantised route: exp2 = E with every |cell| < 2^E, no pivot on the way in
+        top = max(abs(float(lo)), abs(float(hi)))
+        return ST_REGULAR, 0.0, (0 if top == 0 else int(np.frexp(top)[1]))
     p = np.float64(lo * np.float64(0.5)) + np.float64(hi * np.float64(0.5))
     d = max(np.float64(hi - p), np.float64(p - lo))
     e = 0 if d == 0 else int(np.frexp(d)[1])
@@ -462,6 +465,12 @@ def _isum(x: np.ndarray) -> int:
     return sum(int(x[i:i + (1 << 14)].sum(dtype=np.int64)) for i in range(0, len(x), 1 << 14))
 
 
+def _isum_sq(q: np.ndarray) -> int:
+    """exact sum of squares of int64 terms below 2^27 in magnitude (squares below 2^54: 512 of them fit int64)"""
+    sq = q * q
+    return sum(int(sq[i:i + 512].sum(dtype=np.int64)) for i in range(0, len(sq), 512))
+
+
 def integer_route(ct: int) -> bool:
     return is_integral(ct) and size_of(ct) <= 4
 
@@ -474,6 +483,12 @@ def moments_raw(a, mask, pivot: float, exp2: int):
     if integer_route(ct_of(a)):
         xs = [int(v) for v in a]
         return [len(xs), sum(xs), sum(v * v for v in xs), 0, 0]
+    if ct_of(a) == Float32:
+        # Float32 cells are read as the int32 raster q = rint(x * 2^(26 - E)) (half to even; the scaling is exact in f64)
+        # and summed exactly like integer cells
+        with np.errstate(all="ignore"):
+            q = np.rint(np.ldexp(a.astype(np.float64), 26 - exp2)).astype(np.int64)
+        return [len(q), _isum(q), sum(int(v) * int(v) for v in q) if len(q) < (1 << 16) else _isum_sq(q), 0, 0]
     with np.errstate(all="ignore"):
         y = (a.astype(np.float64) - np.float64(pivot)) * np.float64(np.ldexp(1.0, -exp2))
         x1, x2 = _windows(y)
@@ -493,6 +508,14 @@ def statistics_finish(raws, mn: Value, mx: Value):
         lo, hi = _value_f64(mn), _value_f64(mx)
         if not (math.isnan(lo) or math.isnan(hi)) and not (lo == -math.inf and hi == math.inf):
             out["mean"] = lo if lo == -math.inf else hi
+        return out
+    if mn.ct == Float32:
+        # finish the int32 raster of quantised cells (min / max quantise monotonically), scale back by 2^-(26 - E): exact
+        k = 26 - e
+        qmn = value(Int32, int(np.rint(math.ldexp(_value_f64(mn), k))))
+        qmx = value(Int32, int(np.rint(math.ldexp(_value_f64(mx), k))))
+        q = statistics_finish(raws, qmn, qmx)
+        out["mean"], out["stddev"] = math.ldexp(q["mean"], -k), math.ldexp(q["stddev"], -k)
         return out
     n = float(tot[0])
     if integer_route(mn.ct):

@@ -105,5 +105,7 @@ def test_strip_and_grid_independence_at_scale(orc):
         assert (again.count, fbits(again.mean), fbits(again.stddev)) == (whole.count, fbits(whole.mean), fbits(whole.stddev))
         host = buf.to_vec()
         same(whole, orc.statistics(host))
-        assert abs(whole.mean - host.astype(np.float64).mean()) <= 1e-9 * abs(whole.mean) + 1e-9
-        assert abs(whole.stddev - host.astype(np.float64).std()) <= 1e-9 * whole.stddev
+        # Float32 cells are summed on the grid 2^(E - 26): the mean is within half a grid step, in practice far closer
+        slack = 2.0 ** (14 - 26) * 1e-3 if ct == CellType.Float32 else 0.0
+        assert abs(whole.mean - host.astype(np.float64).mean()) <= 1e-9 * abs(whole.mean) + 1e-9 + slack
+        assert abs(whole.stddev - host.astype(np.float64).std()) <= 1e-9 * whole.stddev + slack

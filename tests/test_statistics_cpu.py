@@ -61,6 +61,18 @@ def test_definition_is_accurate(orc, dt, kind):
     # 2 ULP of the mean, or — when the mean is small against the data (cancellation in pivot + offset) — 2 ULP of
     # the largest cell magnitude
     top = float(np.abs(a.astype(np.float64)).max())
+    if dt == "f4":
+        # Float32 cells are summed on the grid 2^(E - 26), 2^E > the largest magnitude: every cell is off by at most half
+        # a grid step (an eighth of the ulp of the largest cells), so mean and stddev are within one grid step
+        grid = 2.0 ** (math.frexp(top)[1] - 26)
+        assert abs(s["mean"] - mean) <= 0.5 * grid + 2 * 2.0 ** -52 * top, (s["mean"], mean)
+        assert abs(s["stddev"] - sd) <= grid + 1e-13 * abs(sd), (s["stddev"], sd)
+        # and exact whenever every cell sits on the grid (all magnitudes within 2^3 of the largest): integers here
+        ints = rng.integers(-4000, 4000, 3000).astype(np.float32)
+        si, (mi, sdi) = orc.statistics(ints), exact(ints)
+        assert ulps(si["mean"], mi) <= 2 or abs(si["mean"] - mi) <= 2 * 2.0 ** -52 * 4000, (si["mean"], mi)
+        assert abs(si["stddev"] - sdi) <= 4e-16 * sdi + 1e-13 * abs(si["stddev"])
+        return
     assert ulps(s["mean"], mean) <= 2 or abs(s["mean"] - mean) <= 2 * 2.0 ** -52 * top, (s["mean"], mean)
     if sd == 0:
         assert s["stddev"] == 0

@@ -79,7 +79,11 @@ static void run_map2(const char* op, const typename F::A* a, const typename F::B
     constexpr size_t TILE = size_t(THREADS) * V * UNROLL;
     for (int cm : kCaps) {
         const int grid = grid_of(n, TILE, cm * g_sms);
-        float ms = time_ms([&] { ++g_it; map2_kernel<F, VB, UNROLL, THREADS><<<grid, THREADS>>>(rot(a, n, g_arena_in), rot(b, n, g_arena_in), rot(o, n, g_arena_out), n, f, lm, rm, om, MaskCount{nullptr, nullptr, 0}); });
+        float ms = time_ms([&] {
+            ++g_it;
+            if (lm) map2_kernel<F, VB, UNROLL, THREADS, true><<<grid, THREADS>>>(rot(a, n, g_arena_in), rot(b, n, g_arena_in), rot(o, n, g_arena_out), n, f, lm, rm, om, MaskCount{nullptr, nullptr, 0});
+            else map2_kernel<F, VB, UNROLL, THREADS, false><<<grid, THREADS>>>(rot(a, n, g_arena_in), rot(b, n, g_arena_in), rot(o, n, g_arena_out), n, f, lm, rm, om, MaskCount{nullptr, nullptr, 0});
+        });
         report(op, VB, UNROLL, THREADS, cm, bpc * n, ms);
     }
 }
