@@ -135,6 +135,16 @@ static cudaStream_t cur_stream() { return (t_dev == 0 && t_stream_set) ? t_strea
 static Launch launch_ctx() {
     return Launch{cur_stream(), g_ctx.prop.multiProcessorCount, g_ctx.max_grid, g_ctx.overlap.load(std::memory_order_relaxed) != 0};
 }
+// Reductions are NOT launched as programmatic dependents: their persistent grid (4-8 CTAs per SM, all resident at
+// once) is scheduled while the grid before it still runs and parks on griddepcontrol.wait holding half of every SM —
+// measured on the NDVI -> min_max chain at 32768^2: 30.3 ms per 8 tiles with the attribute, 25.2 ms without
+// (profiles/r02_pdl_reductions.txt). $EC_PDL_REDUCE_ATTR=1 brings the attribute back for the A/B.
+static Launch launch_ctx_reduce() {
+    static const int attr = env_int("EC_PDL_REDUCE_ATTR", 0);
+    Launch l = launch_ctx();
+    l.overlap = l.overlap && attr;
+    return l;
+}
 int n_devices() { return g_ctx.n_dev; }
 int device_phys(int dev) { return g_ctx.dev[dev].phys; }
 bool shard_policy(size_t n) {
@@ -369,6 +379,8 @@ static ec_status reduce_scratch(ReduceScratch* out, PendingReduce* pend) {
     *out = sc->rs;
     out->px = PeerExchange{nullptr, 0, 0, 0, 0};
     out->host_seq = ++td.seq;
+    static const int trig = env_int("EC_PDL_REDUCE_TRIGGER", 1);
+    out->early_trigger = trig;
     if (pend) *pend = PendingReduce{td.pinned + 8, out->host_seq, cur_stream(), t_dev};
     return EC_OK;
 }
@@ -902,7 +914,7 @@ ec_status min_max_begin(const ec_buf* b, const ec_mask* m, const PeerExchange* p
     ReduceScratch sc;
     EC_TRY(reduce_scratch(&sc, pend));
     if (px) sc.px = *px;
-    EC_LAUNCH(launch_min_max(launch_ctx(), b->ct, rd(b), m ? rdm(m) : nullptr, b->len, sc), px ? "min_max(peer exchange)" : "min_max");
+    EC_LAUNCH(launch_min_max(launch_ctx_reduce(), b->ct, rd(b), m ? rdm(m) : nullptr, b->len, sc), px ? "min_max(peer exchange)" : "min_max");
     if (sc_out) *sc_out = sc;
     return EC_OK;
 }
@@ -911,7 +923,7 @@ ec_status popcount_begin(const ec_mask* m, const PeerExchange* px, uint64_t seco
     ReduceScratch sc;
     EC_TRY(reduce_scratch(&sc, pend));
     if (px) sc.px = *px;
-    EC_LAUNCH(launch_popcount(launch_ctx(), rdm(m), (m->len + 31) / 32, sc, second_word), px ? "mask_counts(peer exchange)" : "mask_counts");
+    EC_LAUNCH(launch_popcount(launch_ctx_reduce(), rdm(m), (m->len + 31) / 32, sc, second_word), px ? "mask_counts(peer exchange)" : "mask_counts");
     return EC_OK;
 }
 ec_status first_diff_begin(const ec_buf* l, const ec_buf* r, size_t n, PendingReduce* pend) {
@@ -920,7 +932,7 @@ ec_status first_diff_begin(const ec_buf* l, const ec_buf* r, size_t n, PendingRe
     EC_TRY(resolve(r));
     ReduceScratch sc;
     EC_TRY(reduce_scratch(&sc, pend));
-    EC_LAUNCH(launch_first_diff(launch_ctx(), (int)kSize[l->ct], rd(l), rd(r), n, sc), "first_diff");
+    EC_LAUNCH(launch_first_diff(launch_ctx_reduce(), (int)kSize[l->ct], rd(l), rd(r), n, sc), "first_diff");
     return EC_OK;
 }
 // first differing bit of two plain masks on the current device, ~0 if none below n
@@ -929,7 +941,7 @@ ec_status mask_first_diff(const ec_mask* l, const ec_mask* r, size_t n, uint64_t
     ReduceScratch sc;
     PendingReduce pend;
     EC_TRY(reduce_scratch(&sc, &pend));
-    EC_LAUNCH(launch_first_diff(launch_ctx(), 4, rdm(l), rdm(r), (n + 31) / 32, sc), "first_diff");
+    EC_LAUNCH(launch_first_diff(launch_ctx_reduce(), 4, rdm(l), rdm(r), (n + 31) / 32, sc), "first_diff");
     uint64_t w, unused;
     EC_TRY(reduce_end(pend, &w, &unused));
     if (w == ~0ull) return EC_OK;

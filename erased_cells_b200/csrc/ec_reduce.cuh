@@ -31,6 +31,7 @@ struct ReduceScratch {
     uint64_t* result;       // 4 words: [0..1] raw result; [2..3] min_max as {skey(min), ~skey(max)} for a MIN all-reduce
     uint64_t* host_result;  // optional device alias of mapped pinned host memory: {r0, r1, host_seq, status}; saves the D2H copy
     uint64_t host_seq;      // tag written last into host_result[2]: the host polls for it instead of synchronising the stream
+    int early_trigger;      // experiment knob: let the next grid be scheduled at once (griddepcontrol.launch_dependents) or only when this one ends
     PeerExchange px;
 };
 
@@ -164,7 +165,8 @@ __global__ void __launch_bounds__(THREADS) min_max_kernel(const T* __restrict__ 
     constexpr size_t TILE = size_t(THREADS) * V * UNROLL;
     const size_t full = n / TILE;
     K kmin = seed_min, kmax = seed_max;
-    overlap_prologue();
+    if (s.early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if constexpr (MASKED && sizeof(T) == 1 && VB == 32) {
         // 8-bit cells with a mask: a thread's 32 cells are exactly one mask word. Invalid bytes are forced to the
@@ -289,7 +291,8 @@ __global__ void __launch_bounds__(THREADS) popcount_kernel(const uint32_t* __res
                                                            uint64_t second_word) {
     uint64_t c = 0;
     const size_t groups = words / 4;  // 16-byte groups (allocation is padded to 16 bytes, pad is zero)
-    overlap_prologue();
+    if (s.early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (size_t g = blockIdx.x * size_t(THREADS) + threadIdx.x; g < groups; g += size_t(gridDim.x) * THREADS) {
         const Vec<uint32_t, 4> w = ld_stream<uint32_t, 4>(m + 4 * g);
         c += __popc(w.v[0]) + __popc(w.v[1]) + __popc(w.v[2]) + __popc(w.v[3]);
@@ -307,7 +310,8 @@ __global__ void __launch_bounds__(THREADS) first_diff_kernel(const T* __restrict
     constexpr int V = VB / sizeof(T);
     uint64_t first = ~0ull;
     const size_t groups = n / V;
-    overlap_prologue();
+    if (s.early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // compare 32 bytes as four 64-bit words; only a differing word is examined cell by cell (lowest differing byte)
     for (size_t g = blockIdx.x * size_t(THREADS) + threadIdx.x; g < groups; g += size_t(gridDim.x) * THREADS) {
         const Raw<VB> x = ld_stream_raw<VB>(a + g * V), y = ld_stream_raw<VB>(b + g * V);
