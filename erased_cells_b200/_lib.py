@@ -91,6 +91,8 @@ def _signatures():
         "ec_set_shard_min_cells": (SZ, [SZ]),
         "ec_set_shard_finish": (I, [I]),
         "ec_set_min_max_cache": (I, [I]),
+        "ec_set_reduce_trace": (I, [I]),
+        "ec_reduce_trace_get": (S, [C.POINTER(U64)]),
         "ec_buf_shard_count": (I, [VP]),
         "ec_mask_shard_count": (I, [VP]),
         "ec_buf_shard": (S, [VP, I, C.POINTER(ShardInfo), PVP]),

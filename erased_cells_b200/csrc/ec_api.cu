@@ -112,7 +112,7 @@ struct StreamScratch {
 };
 struct ThreadDev {
     std::vector<StreamScratch> per_stream;
-    uint64_t* pinned = nullptr;      // 32 words of pinned, device-mapped host memory: [0..3] single cells / keys, [8..11] reduction results, [16..24] statistics sums
+    uint64_t* pinned = nullptr;      // 64 words of pinned, device-mapped host memory: [0..4] single cells / keys, [8..12] reduction results, [16..24] statistics sums, [32..39] trace stamps
     uint64_t* pinned_dev = nullptr;  // its device alias: reduction kernels write results [8..11] straight into it
     uint64_t seq = 0;                // tag of the last result asked for
 };
@@ -342,8 +342,8 @@ static ec_status sync_stream() {
 static ec_status pinned_words(uint64_t** out) {
     ThreadDev& td = t_td[t_dev];
     if (!td.pinned) {
-        if (cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&td.pinned), 256, cudaHostAllocMapped | cudaHostAllocPortable)) return cuda_fail(e, "cudaHostAlloc");
-        memset(td.pinned, 0, 256);
+        if (cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&td.pinned), 512, cudaHostAllocMapped | cudaHostAllocPortable)) return cuda_fail(e, "cudaHostAlloc");
+        memset(td.pinned, 0, 512);
         if (cudaError_t e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&td.pinned_dev), td.pinned, 0)) return cuda_fail(e, "cudaHostGetDevicePointer");
     }
     *out = td.pinned;
@@ -371,6 +371,15 @@ static ec_status stream_scratch(StreamScratch** out) {
     *out = &td.per_stream.back();
     return EC_OK;
 }
+// ---- where the time of one reduction call goes (ec_set_reduce_trace) ---------------------------------------------------
+static std::atomic<int> g_reduce_trace{0};
+static thread_local uint64_t t_trace_host[3];  // call entered, launch returned, result seen (CLOCK_REALTIME ns)
+static thread_local const uint64_t* t_trace_gpu = nullptr;
+static uint64_t host_ns() {
+    timespec t;
+    clock_gettime(CLOCK_REALTIME, &t);
+    return uint64_t(t.tv_sec) * 1000000000ull + uint64_t(t.tv_nsec);
+}
 // scratch of a reduction launched now on the current stream, its result tagged with a fresh sequence number
 static ec_status reduce_scratch(ReduceScratch* out, PendingReduce* pend) {
     StreamScratch* sc;
@@ -378,9 +387,15 @@ static ec_status reduce_scratch(ReduceScratch* out, PendingReduce* pend) {
     ThreadDev& td = t_td[t_dev];
     *out = sc->rs;
     out->px = PeerExchange{nullptr, 0, 0, 0, 0};
-    out->host_seq = ++td.seq;
+    out->host_seq = 0x80000000ull | (++td.seq & 0x7FFFFFFFull);
     static const int trig = env_int("EC_PDL_REDUCE_TRIGGER", 1);
     out->early_trigger = trig;
+    out->trace = nullptr;
+    if (g_reduce_trace) {
+        for (int i = 32; i < 40; ++i) td.pinned[i] = 0;
+        out->trace = td.pinned_dev + 32;
+        t_trace_host[0] = host_ns();
+    }
     if (pend) *pend = PendingReduce{td.pinned + 8, out->host_seq, cur_stream(), t_dev};
     return EC_OK;
 }
@@ -406,11 +421,37 @@ static ec_status poll_tag(volatile uint64_t* tag_word, uint64_t tag, cudaStream_
         }
     }
 }
+// wait until all five words of a published result carry the call's tag (see block_finish in ec_reduce.cuh)
+static ec_status poll_result(const PendingReduce& p) {
+    const uint64_t tag = p.seq << 32;
+    for (unsigned long spins = 0;; ++spins) {
+        bool all = true;
+        for (int i = 0; i < 5; ++i) all = all && ((p.pin[i] ^ tag) >> 32) == 0;
+        if (all) { std::atomic_thread_fence(std::memory_order_acquire); return EC_OK; }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if ((spins & 0x3FFF) == 0x3FFF) {
+            PhysGuard g(p.dev);
+            const cudaError_t q = cudaStreamQuery(p.stream);
+            if (q == cudaSuccess) {
+                all = true;
+                for (int i = 0; i < 5; ++i) all = all && ((p.pin[i] ^ tag) >> 32) == 0;
+                if (all) return EC_OK;
+                set_error("a reduction kernel finished without publishing its result");
+                return EC_CUDA;
+            }
+            if (q != cudaErrorNotReady) return cuda_fail(q, "cudaStreamQuery");
+        }
+    }
+}
 ec_status reduce_end(const PendingReduce& p, uint64_t* r0, uint64_t* r1) {
-    if (ec_status s = poll_tag(p.pin + 2, p.seq, p.stream, p.dev)) return s;
-    *r0 = p.pin[0];
-    *r1 = p.pin[1];
-    if (p.pin[3] != 0) { set_error("a peer GPU did not deliver its partial result within the spin limit"); return EC_NCCL; }
+    if (g_reduce_trace) t_trace_host[1] = host_ns();
+    if (ec_status s = poll_result(p)) return s;
+    if (g_reduce_trace) { t_trace_host[2] = host_ns(); t_trace_gpu = const_cast<const uint64_t*>(p.pin) + 24; }
+    *r0 = (p.pin[0] & 0xFFFFFFFFull) | (p.pin[1] << 32);
+    *r1 = (p.pin[2] & 0xFFFFFFFFull) | (p.pin[3] << 32);
+    if ((p.pin[4] & 0xFFFFFFFFull) != 0) { set_error("a peer GPU did not deliver its partial result within the spin limit"); return EC_NCCL; }
     return EC_OK;
 }
 
@@ -1181,6 +1222,36 @@ size_t ec_set_shard_min_cells(size_t cells) { return g_ctx.shard_min_cells.excha
 int ec_set_shard_finish(int mode) {
     if (mode < FINISH_HOST || mode > FINISH_NCCL) return -1;
     return g_ctx.finish.exchange(mode);
+}
+int ec_set_reduce_trace(int on) { return g_reduce_trace.exchange(on != 0); }
+__global__ void globaltimer_probe(volatile uint64_t* out) {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    out[0] = t;
+}
+ec_status ec_reduce_trace_get(uint64_t* out12) {
+    EC_TRY(ensure());
+    if (!t_trace_gpu) return invalid("ec_reduce_trace_get: no traced reduction on this thread yet");
+    for (int i = 0; i < 3; ++i) out12[i] = t_trace_host[i];
+    for (int i = 0; i < 6; ++i) out12[3 + i] = t_trace_gpu[i];
+    // offset of %globaltimer against CLOCK_REALTIME: a one-thread kernel stamps mapped memory, the host notes when it sees
+    // the stamp; the smallest (host - gpu) over a few tries is the offset plus the ~1 us it takes the stamp to arrive
+    uint64_t* pin;
+    EC_TRY(pinned_words(&pin));
+    ThreadDev& td = t_td[t_dev];
+    int64_t best = INT64_MAX;
+    for (int rep = 0; rep < 20; ++rep) {
+        pin[4] = 0;
+        globaltimer_probe<<<1, 1, 0, cur_stream()>>>(td.pinned_dev + 4);
+        volatile uint64_t* w = pin + 4;
+        while (*w == 0) {}
+        const int64_t d = static_cast<int64_t>(host_ns()) - static_cast<int64_t>(*w);
+        if (d < best) best = d;
+    }
+    EC_TRY(sync_stream());
+    out12[9] = static_cast<uint64_t>(best);
+    out12[10] = out12[11] = 0;
+    return EC_OK;
 }
 ec_status ec_device_info_get(ec_device_info* out) {
     EC_TRY(ensure());

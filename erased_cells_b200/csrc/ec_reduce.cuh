@@ -16,7 +16,7 @@ namespace ec {
 // that folds this GPU's partials also exchanges the 16-byte partial result with every peer — remote stores into
 // each peer's mailbox, then a bounded spin on its own mailbox — and reduces the n_ranks pairs, so a sharded
 // reduction is ONE kernel per GPU with no separate collective launch. Mailbox slot (32 bytes) of sender r for
-// epoch e lives at word 4 * ((e & 1) * n_ranks + r): {value0, value1, epoch, pad}. Two epochs of slots suffice:
+// epoch e lives at word 4 * ((e & 1) * n_ranks + r): four words {tag(e) | 32 payload bits}. Two epochs of slots suffice:
 // a rank can only be one collective ahead of the slowest peer, because finishing epoch e needs every peer's
 // epoch-e message.
 struct PeerExchange {
@@ -29,12 +29,23 @@ struct ReduceScratch {
     uint64_t* partials;     // 2 * max_blocks
     unsigned int* ticket;   // zero between launches (the finishing CTA resets it)
     uint64_t* result;       // 4 words: [0..1] raw result; [2..3] min_max as {skey(min), ~skey(max)} for a MIN all-reduce
-    uint64_t* host_result;  // optional device alias of mapped pinned host memory: {r0, r1, host_seq, status}; saves the D2H copy
-    uint64_t host_seq;      // tag written last into host_result[2]: the host polls for it instead of synchronising the stream
+    uint64_t* host_result;  // optional device alias of mapped pinned host memory: five words {tag | 32 bits}: r0 lo/hi, r1 lo/hi, status
+    uint64_t host_seq;      // the 32-bit tag of this call (top bit set): the host polls for it instead of synchronising the stream
     int early_trigger;      // experiment knob: let the next grid be scheduled at once (griddepcontrol.launch_dependents) or only when this one ends
+    uint64_t* trace;        // null, or 8 words of mapped pinned memory the kernel stamps with %globaltimer (ec_set_reduce_trace): where a call's time goes
     PeerExchange px;
 };
 
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// trace slots: 0 first CTA past the dependency wait, 1 last CTA of the grid has its partial, 2 this GPU's result folded,
+// 3 partial sent to every peer, 4 every peer's partial received and folded, 5 result published to the host
+__device__ __forceinline__ void stamp(const ReduceScratch& s, int slot) {
+    if (s.trace != nullptr) { volatile uint64_t* t = s.trace; t[slot] = global_ns(); }
+}
 __device__ __forceinline__ uint32_t warp_min(uint32_t v) { return __reduce_min_sync(0xFFFFFFFFu, v); }
 __device__ __forceinline__ uint32_t warp_max(uint32_t v) { return __reduce_max_sync(0xFFFFFFFFu, v); }
 __device__ __forceinline__ uint64_t warp_min(uint64_t v) {
@@ -82,6 +93,7 @@ __device__ __forceinline__ void block_finish(uint64_t k0, uint64_t k1, uint64_t 
     __syncthreads();
     if (!last) return;
     __threadfence();
+    if (threadIdx.x == 0) stamp(s, 1);
     uint64_t a0 = id0, a1 = id1;
     for (unsigned int i = threadIdx.x; i < gridDim.x; i += THREADS) {
         combine<MODE>(a0, a1, __ldcg(s.partials + 2 * i), __ldcg(s.partials + 2 * i + 1));
@@ -100,36 +112,45 @@ __device__ __forceinline__ void block_finish(uint64_t k0, uint64_t k1, uint64_t 
         for (int w = 1; w < THREADS / 32; ++w) combine<MODE>(a0, a1, sh0[w], sh1[w]);
         xr[0] = a0; xr[1] = a1;
         xstatus = 0;
+        stamp(s, 2);
     }
     if (s.px.peers != nullptr) {
         // ---- exchange with the peer GPUs (uniform branch: every thread of the CTA takes it) ----
+        // A message is four 64-bit words, each carrying 32 bits of payload under a 32-bit tag made from the epoch: a word
+        // is valid exactly when its tag is the current one, and an aligned 64-bit store arrives whole — so the sender
+        // needs no system-scope fence between "data" and "flag" (there is no separate flag), and the receiver simply
+        // polls until all four tags match. One NVLink crossing instead of a fenced round trip plus a crossing.
         __syncthreads();
         const int n = s.px.n_ranks;
         const unsigned long long base = 4ull * ((s.px.epoch & 1ull) * n);
+        const unsigned long long tag = (0x80000000ull | (s.px.epoch & 0x7FFFFFFFull)) << 32;
         if (threadIdx.x < n) {  // thread t talks to rank t: send ...
             volatile unsigned long long* slot = s.px.peers[threadIdx.x] + base + 4ull * s.px.rank;
-            slot[0] = xr[0];
-            slot[1] = xr[1];
-            __threadfence_system();
-            slot[2] = s.px.epoch;
+            slot[0] = tag | (xr[0] & 0xFFFFFFFFull);
+            slot[1] = tag | (xr[0] >> 32);
+            slot[2] = tag | (xr[1] & 0xFFFFFFFFull);
+            slot[3] = tag | (xr[1] >> 32);
+            if (threadIdx.x == 0) stamp(s, 3);
         }
         uint64_t p0 = id0, p1 = id1;
         if (threadIdx.x < n) {  // ... then receive rank t's partial from our own mailbox
             volatile unsigned long long* slot = s.px.peers[s.px.rank] + base + 4ull * threadIdx.x;
             const long long t0 = clock64();
             bool ok = true;
-            while (slot[2] != s.px.epoch) {
+            unsigned long long w0, w1, w2, w3;
+            for (;;) {
+                w0 = slot[0]; w1 = slot[1]; w2 = slot[2]; w3 = slot[3];
+                if (((w0 ^ tag) >> 32) == 0 && ((w1 ^ tag) >> 32) == 0 && ((w2 ^ tag) >> 32) == 0 && ((w3 ^ tag) >> 32) == 0) break;
                 if (static_cast<unsigned long long>(clock64() - t0) > s.px.spin_limit) { ok = false; break; }
             }
-            __threadfence_system();
-            if (ok) { p0 = slot[0]; p1 = slot[1]; } else { atomicOr(&xstatus, 1u); }
+            if (ok) { p0 = (w0 & 0xFFFFFFFFull) | (w1 << 32); p1 = (w2 & 0xFFFFFFFFull) | (w3 << 32); } else { atomicOr(&xstatus, 1u); }
         }
         // fold the n_ranks pairs (n_ranks <= 32: one warp)
         if (threadIdx.x < 32) {
             if constexpr (MODE == RED_MINMAX) { p0 = warp_min(p0); p1 = warp_max(p1); }
             else if constexpr (MODE == RED_SUM) { p0 = warp_sum(p0); p1 = warp_sum(p1); }
             else { p0 = warp_min(p0); p1 = warp_min(p1); }
-            if (threadIdx.x == 0) { xr[0] = p0; xr[1] = p1; }
+            if (threadIdx.x == 0) { xr[0] = p0; xr[1] = p1; stamp(s, 4); }
         }
         __syncthreads();
     }
@@ -141,13 +162,17 @@ __device__ __forceinline__ void block_finish(uint64_t k0, uint64_t k1, uint64_t 
             s.result[2] = a0 ^ 0x8000000000000000ull;
             s.result[3] = ~(a1 ^ 0x8000000000000000ull);
         }
-        if (s.host_result != nullptr) {  // mapped pinned memory: the host polls word 2 for its tag, no D2H copy, no stream sync
+        if (s.host_result != nullptr) {
+            // mapped pinned memory, same self-validating layout: five words {tag | 32 payload bits} — a0, a1 in halves and
+            // the status. The host polls until all five carry this call's tag: no D2H copy, no stream sync, no fence.
             volatile uint64_t* hr = s.host_result;
-            hr[0] = a0;
-            hr[1] = a1;
-            hr[3] = xstatus;
-            __threadfence_system();
-            hr[2] = s.host_seq;
+            const uint64_t htag = s.host_seq << 32;
+            hr[0] = htag | (a0 & 0xFFFFFFFFull);
+            hr[1] = htag | (a0 >> 32);
+            hr[2] = htag | (a1 & 0xFFFFFFFFull);
+            hr[3] = htag | (a1 >> 32);
+            hr[4] = htag | xstatus;
+            stamp(s, 5);
         }
         *s.ticket = 0;  // ready for the next launch on this stream
     }
@@ -167,6 +192,7 @@ __global__ void __launch_bounds__(THREADS) min_max_kernel(const T* __restrict__ 
     K kmin = seed_min, kmax = seed_max;
     if (s.early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (blockIdx.x == 0 && threadIdx.x == 0) stamp(s, 0);
 
     if constexpr (MASKED && sizeof(T) == 1 && VB == 32) {
         // 8-bit cells with a mask: a thread's 32 cells are exactly one mask word. Invalid bytes are forced to the

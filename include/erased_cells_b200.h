@@ -137,6 +137,14 @@ ec_status ec_trim(void);
 uint64_t ec_guard_violations(void);
 size_t ec_cached_bytes(void);
 uint64_t ec_kernel_launches(void);       /* number of this library's kernels launched so far */
+/* Where the time of one reduction call goes (profiling aid, off by default). With tracing on, ec_buf_min_max and the
+ * sharded reductions stamp %globaltimer inside the kernel; ec_reduce_trace_get returns, for the calling thread's last
+ * call, in ns: [0] call entered, [1] launch returned, [2] result seen by the host (CLOCK_REALTIME); [3] first CTA
+ * running, [4] last CTA of the grid done, [5] this GPU's result folded, [6] partial sent to the peers, [7] peers'
+ * partials received, [8] result published (%globaltimer; 0 = stage not reached); [9] offset to add to a %globaltimer
+ * value to compare it with CLOCK_REALTIME (calibrated on the spot, good to about a microsecond). */
+int ec_set_reduce_trace(int on);
+ec_status ec_reduce_trace_get(uint64_t out12[12]);
 /* name of the last kernel family launched by this thread (for profiles/bench bookkeeping) */
 const char* ec_last_kernel(void);
 ec_status ec_event_create(ec_event** out);

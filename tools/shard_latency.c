@@ -34,6 +34,7 @@ int main(int argc, char** argv) {
     for (const char* p = list; *p && n < 16;) { char* e; devs[n++] = (int)strtol(p, &e, 10); p = *e == ',' ? e + 1 : e; }
     const int iters = argc > 3 ? atoi(argv[3]) : 50;
     CK(ec_init_devices(devs, n));
+    ec_set_min_max_cache(0);  /* every timed call reads the raster */
     ec_set_shard_min_cells((size_t)1 << 20);
     const size_t cells = side * side;
     ec_buf* a;
