@@ -142,6 +142,11 @@ def _signatures():
         "ec_buf_from_host": (S, [U8, VP, SZ, PVP]),
         "ec_buf_from_host_async": (S, [U8, VP, SZ, PVP]),
         "ec_buf_wait": (S, [VP]),
+        "ec_ingest_begin": (S, [U8, SZ, I, PV, I, SZ, PVP]),
+        "ec_ingest_next_buffer": (S, [VP, PVP, PSZ]),
+        "ec_ingest_submit": (S, [VP, SZ]),
+        "ec_ingest_finish": (S, [VP, PVP, PVP]),
+        "ec_ingest_abort": (None, [VP]),
         "ec_buf_with_defaults": (S, [SZ, U8, PVP]),
         "ec_buf_fill": (S, [SZ, PV, PVP]),
         "ec_buf_wrap_device": (S, [U8, VP, SZ, PVP]),

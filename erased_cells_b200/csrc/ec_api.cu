@@ -1280,8 +1280,10 @@ ec_status ec_synchronize(void) {
     }
     return sync_stream();
 }
+namespace ec { void stage_pool_trim(); }
 ec_status ec_trim(void) {
     EC_TRY(ec_synchronize());
+    stage_pool_trim();
     for (int g = 0; g < g_ctx.n_dev; ++g) {
         PhysGuard pg(g);
         std::lock_guard<std::mutex> lk(g_ctx.dev[g].cache.mu);
@@ -2421,3 +2423,4 @@ ec_status ec_buf_synth(uint8_t ct, size_t len, uint64_t seed, uint64_t index_off
 
 }  // extern "C"
 #include "ec_shard.inc"
+#include "ec_ingest.inc"

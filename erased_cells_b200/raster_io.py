@@ -110,15 +110,140 @@ def write_tiff(path: str, px: np.ndarray, nodata: float | None = None, rows_per_
     open(path, "wb").write(bytes(out))
 
 
-def read_cells(path: str, wait: bool = False) -> CellBuffer:
+class Ingest:
+    """A raster arriving chunk by chunk (ec_ingest_*): the reader fills pinned staging buffers in turn; the upload of one
+    chunk, the reader's work on the next and the NoData compare of the previous one overlap. `nodata=None` with
+    `masked=False` is RasterBandEx::read_cells, a NoData with `masked=True` is read_cells_masked."""
+
+    def __init__(self, ct: CellType, len_: int, nodata: NoData | None = None, masked: bool = False, chunk_cells: int = 0):
+        import ctypes as C
+
+        from ._lib import check, lib
+        self._C, self._check, self._lib = C, check, lib()
+        self.ct, self.len, self.masked = CellType(ct), len_, masked
+        nd = nodata if nodata is not None else NoData.none(self.ct)
+        h = C.c_void_p()
+        check(self._lib.ec_ingest_begin(int(self.ct), len_, nd.kind, nd._ptr(), int(masked), chunk_cells, C.byref(h)))
+        self._h = h
+
+    def next_buffer(self):
+        """a numpy view of the next pinned staging buffer (None once every cell is in); fill a prefix, then submit(n)"""
+        C = self._C
+        p, cap = C.c_void_p(), C.c_size_t()
+        self._check(self._lib.ec_ingest_next_buffer(self._h, C.byref(p), C.byref(cap)))
+        if not cap.value:
+            return None
+        raw = (C.c_uint8 * (cap.value * self.ct.size_of())).from_address(p.value)
+        return np.frombuffer(raw, dtype=self.ct.dtype)
+
+    def submit(self, n_cells: int) -> None:
+        self._check(self._lib.ec_ingest_submit(self._h, n_cells))
+
+    def finish(self):
+        C = self._C
+        b, m = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.ec_ingest_finish(self._h, C.byref(b), C.byref(m) if self.masked else None))
+        self._h = None
+        buf = CellBuffer._take(b)
+        if not self.masked:
+            return buf
+        from .api import Mask
+        return MaskedCellBuffer(buf, Mask._take(m))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.ec_ingest_abort(self._h)
+
+
+def ingest(cells: np.ndarray, nodata: NoData | None = None, masked: bool = False, chunk_cells: int = 0):
+    """Upload a host array (pageable is fine) through the chunked pipeline: each chunk is copied into pinned staging by the
+    host while the previous one crosses PCIe and the one before gets its mask built."""
+    a = np.ascontiguousarray(cells).reshape(-1)
+    g = Ingest(CellType.of(a), a.size, nodata, masked, chunk_cells)
+    pos = 0
+    while True:
+        buf = g.next_buffer()
+        if buf is None:
+            break
+        n = min(buf.size, a.size - pos)
+        buf[:n] = a[pos:pos + n]
+        g.submit(n)
+        pos += n
+    return g.finish()
+
+
+def _tiff_layout(path: str):
+    """(cell type, width, height, [(file offset, byte count)] of the strips, byte order, GDAL_NODATA) without reading pixels"""
+    with open(path, "rb") as f:
+        b = f.read(1 << 20)  # header + IFD + strip tables of the fixtures live in the first MiB
+    bo = {b"II": "<", b"MM": ">"}[b[:2]]
+    (ifd,) = struct.unpack(bo + "I", b[4:8])
+    (n,) = struct.unpack(bo + "H", b[ifd:ifd + 2])
+    tsz = {1: 1, 2: 1, 3: 2, 4: 4, 5: 8, 12: 8, 16: 8}
+    tfmt = {1: "B", 2: "c", 3: "H", 4: "I", 12: "d", 16: "Q"}
+    tags = {}
+    for i in range(n):
+        e = b[ifd + 2 + 12 * i: ifd + 14 + 12 * i]
+        tag, typ, cnt = struct.unpack(bo + "HHI", e[:8])
+        size = tsz.get(typ, 1) * cnt
+        data = e[8:8 + size] if size <= 4 else b[struct.unpack(bo + "I", e[8:12])[0]:][:size]
+        if typ in tfmt and len(data) == size:
+            tags[tag] = struct.unpack(bo + tfmt[typ] * cnt, data)
+    if tags.get(259, (1,)) != (1,) or tags.get(277, (1,)) != (1,):
+        raise UnsupportedCellTypeError("only uncompressed single-band TIFFs")
+    key = (tags.get(339, (1,))[0], tags[258][0])
+    if key not in _TIFF_TYPES:
+        raise UnsupportedCellTypeError(f"sample format {key}")
+    nodata = None
+    if 42113 in tags:
+        txt = b"".join(tags[42113]).split(b"\0")[0].decode().strip()
+        nodata = float(txt) if txt else None
+    return _TIFF_TYPES[key], tags[256][0], tags[257][0], list(zip(tags[273], tags[279])), bo, nodata
+
+
+def _read_streaming(path: str, masked: bool, chunk_cells: int):
+    """the TIFF's strips straight into the pinned staging buffers of a chunked ingest: the file read of chunk k + 1 overlaps
+    the PCIe copy of chunk k and the mask kernel of chunk k - 1 (no assembled host copy of the band)"""
+    ct, width, height, strips, bo, nodata = _tiff_layout(path)
+    nd = nodata_from_gdal(nodata, ct) if masked else None
+    g = Ingest(ct, width * height, nd, masked, chunk_cells)
+    sz = ct.size_of()
+    with open(path, "rb", buffering=0) as f:
+        si, so = 0, 0  # current strip, bytes of it already consumed
+        while True:
+            buf = g.next_buffer()
+            if buf is None:
+                break
+            raw, filled = buf.view(np.uint8), 0
+            while filled < raw.size and si < len(strips):
+                off, cnt = strips[si]
+                take = min(cnt - so, raw.size - filled)
+                f.seek(off + so)
+                got = f.readinto(memoryview(raw[filled:filled + take]))
+                if got != take:
+                    raise ValueError("truncated TIFF")
+                filled += take
+                so += take
+                if so == cnt:
+                    si, so = si + 1, 0
+            n = filled // sz
+            if bo == ">" and sz > 1:
+                buf[:n] = buf[:n].byteswap()
+            g.submit(n)
+    return g.finish()
+
+
+def read_cells(path: str, wait: bool = False, chunk_cells: int = 0) -> CellBuffer:
     """RasterBandEx::read_cells (src/gdal/rasterband.rs:82-103): the band as a device CellBuffer; nodata is ignored.
-    The upload is asynchronous (upload stream); consumers are ordered after it."""
-    px, _ = read_tiff(path)
-    return CellBuffer.from_vec(px.reshape(-1), wait=wait)
+    Strips are streamed through pinned staging (Ingest); consumers are stream-ordered after the uploads."""
+    b = _read_streaming(path, False, chunk_cells)
+    return b.wait() if wait else b
 
 
-def read_cells_masked(path: str, wait: bool = False) -> MaskedCellBuffer:
-    """RasterBandEx::read_cells_masked (src/gdal/rasterband.rs:104-126): GDAL nodata -> NoData<T> -> mask on the device."""
-    px, nodata = read_tiff(path)
-    buf = CellBuffer.from_vec(px.reshape(-1), wait=wait)
-    return MaskedCellBuffer.from_buffer_with_nodata(buf, nodata_from_gdal(nodata, buf.cell_type()))
+def read_cells_masked(path: str, wait: bool = False, chunk_cells: int = 0) -> MaskedCellBuffer:
+    """RasterBandEx::read_cells_masked (src/gdal/rasterband.rs:104-126): GDAL nodata -> NoData<T> -> mask built on the device
+    chunk by chunk while the next chunk is still on its way."""
+    m = _read_streaming(path, True, chunk_cells)
+    if wait:
+        m.buffer().wait()
+    return m

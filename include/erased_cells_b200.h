@@ -92,6 +92,7 @@ enum { EC_STATS_REGULAR = 0, EC_STATS_EMPTY = 1, EC_STATS_NONFINITE = 2 };
 typedef struct ec_buf ec_buf;   /* CellBuffer: typed cells in HBM */
 typedef struct ec_mask ec_mask; /* Mask: validity bits in HBM, packed 32 cells per little-endian word */
 typedef struct ec_event ec_event;
+typedef struct ec_ingest ec_ingest; /* a raster arriving chunk by chunk (ec_ingest_*) */
 typedef struct ec_shard_info ec_shard_info;
 typedef struct ec_comm ec_comm;
 
@@ -190,6 +191,21 @@ ec_status ec_buf_from_host(uint8_t ct, const void* host, size_t len, ec_buf** ou
  * ec_buf_wait() returns — from_vec(Vec<T>) owns its Vec, so the Rust shim parks it in the buffer until then. */
 ec_status ec_buf_from_host_async(uint8_t ct, const void* host, size_t len, ec_buf** out);
 ec_status ec_buf_wait(const ec_buf* b);
+/* Chunked ingest — the step in front of the path (RasterBandEx::read_cells / read_cells_masked, src/gdal/rasterband.rs:81-126,
+ * feed whole bands to from_vec / from_vec_with_nodata). A reader that produces the band piece by piece asks for a pinned
+ * staging buffer, fills it and submits it; the H2D copy of chunk k runs on the upload stream while the reader fills chunk
+ * k + 1 and the NoData compare of chunk k - 1 writes packed mask words on the compute stream. `with_mask` = also build
+ * the MaskedCellBuffer's mask (kind NONE: all valid). chunk_cells = 0 picks 32 MiB chunks; it is rounded up to a multiple
+ * of 128 cells. On a multi-GPU library every chunk goes to the GPU that owns its row strip, over that GPU's own link.
+ *   ec_ingest_begin -> { ec_ingest_next_buffer (blocks until that staging buffer is free; capacity 0 = all cells in),
+ *                        fill, ec_ingest_submit(n <= capacity; short chunks a multiple of 128 cells unless last) }*
+ *                   -> ec_ingest_finish (hands over buffer and mask; nothing is waited for: consumers are stream-ordered) */
+ec_status ec_ingest_begin(uint8_t ct, size_t len, int nodata_kind, const ec_value* value_or_null, int with_mask, size_t chunk_cells,
+                          ec_ingest** out);
+ec_status ec_ingest_next_buffer(ec_ingest* g, void** host_chunk, size_t* capacity_cells);
+ec_status ec_ingest_submit(ec_ingest* g, size_t n_cells);
+ec_status ec_ingest_finish(ec_ingest* g, ec_buf** out_buf, ec_mask** out_mask_or_null);
+void ec_ingest_abort(ec_ingest* g);
 /* with_defaults (:68-77) */
 ec_status ec_buf_with_defaults(size_t len, uint8_t ct, ec_buf** out);
 /* fill (:79-88): type = the value's type */

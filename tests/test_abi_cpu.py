@@ -4,6 +4,7 @@ fail loudly (no CPU fallback) when no GPU is present. No device compute here."""
 import ctypes as C
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -171,3 +172,50 @@ def test_jit_kernels_build_for_sm100a_without_a_gpu():
     expr = b"ecj_add(ecj_add(ecj_add(v0, v1), ecj_add(v2, v3)), ecj_add(ecj_add(v4, v5), ecj_add(v6, v7)))"
     assert L.ec_jit_dry_build(cts, 8, 0, expr, log, len(log)) == _lib.EC_OK, log.value.decode()
     assert L.ec_jit_dry_build(cts, 2, 0, b"not_a_function(v0, v1)", log, len(log)) == _lib.EC_INVALID_ARG and b"not_a_function" in log.value
+
+
+def test_rust_ffi_and_ctypes_bindings_match_the_header():
+    """rust/ffi.rs is generated from include/erased_cells_b200.h (tools/gen_ffi_rs.py): it must be up to date, declare
+    every function of the header with the header's arity and types, and the ctypes binding the tests drive must agree with
+    the same prototypes — so neither host binding can drift from the C ABI unnoticed."""
+    import ctypes as C
+    import re
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_ffi_rs as gen
+    from erased_cells_b200 import _lib
+
+    header = open(gen.HEADER).read()
+    assert open(gen.OUT).read() == gen.generate(), "rust/ffi.rs is stale: python tools/gen_ffi_rs.py"
+    protos = gen.prototypes(header)
+    assert len(protos) >= 120 and len({n for n, _, _ in protos}) == len(protos)
+    rust = open(gen.OUT).read()
+    decl = dict(re.findall(r"pub fn (ec_\w+)\((.*?)\)(?: -> [^;]+)?;", rust))
+    L = ec.lib()
+    sigs = _lib._signatures()
+    assert set(sigs) == {n for n, _, _ in protos}, set(sigs) ^ {n for n, _, _ in protos}
+    scalar = {"int": C.c_int, "uint8_t": C.c_uint8, "uint64_t": C.c_uint64, "int64_t": C.c_int64, "size_t": C.c_size_t,
+              "double": C.c_double, "float": C.c_float, "ec_status": C.c_int}
+
+    def size_class(ctype_c):
+        """what the calling convention sees: pointer, or a scalar of a given ctypes type"""
+        c = ctype_c.replace(" *", "*").strip()
+        if c.endswith("*"):
+            return "ptr"
+        return scalar[c.replace("const ", "").strip()]
+
+    def py_class(t):
+        if t is None:
+            return None
+        if t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or issubclass(t, C._Pointer):
+            return "ptr"
+        return t
+
+    for name, ret, args in protos:
+        assert hasattr(L, name), f"{name} is declared in the header but not exported"
+        n_rust = 0 if not decl[name].strip() else decl[name].count(":")
+        assert n_rust == len(args), (name, decl[name], args)
+        res, argtypes = sigs[name]
+        assert len(argtypes) == len(args), (name, argtypes, args)
+        for (ctype_c, pname), at in zip(args, argtypes):
+            assert size_class(ctype_c) == py_class(at), (name, pname, ctype_c, at)
+        assert (None if ret == "void" else size_class(ret)) == py_class(res), (name, ret, res)

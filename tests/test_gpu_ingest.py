@@ -68,3 +68,36 @@ def test_serde_wire_format():
     assert back.cell_type() == CellType.Float64 and back.mask() == m.mask() and back.get(0) == CellValue.new(0.5)
     assert ec.from_serde(CellBuffer, json.loads('{"UInt16": [7, 8]}')) == CellBuffer.from_vec(np.array([7, 8], np.uint16))
     assert ec.to_serde(NoData.default(CellType.UInt8)) == "Default" and ec.to_serde(NoData.new(CellType.Int16, 3)) == {"Value": 3}
+
+
+@pytest.mark.gpu
+def test_chunked_ingest_matches_one_shot_upload(orc, tmp_path):
+    """ec_ingest_*: a band arriving in chunks (ragged last chunk, chunk sizes from one tile to many, every cell type,
+    NoData None / Default / Value) gives the same buffer, mask and counts as from_vec / from_vec_with_nodata, and the same
+    mask as the oracle; the streaming TIFF reader agrees with the whole-file reader."""
+    rng = np.random.default_rng(11)
+    for ct in CellType:
+        n = 3 * 40960 + 777
+        a = np.frombuffer(rng.bytes(n * ct.size_of()), dtype=ct.dtype).copy()
+        sentinel = a[5]
+        a[rng.integers(0, n, 500)] = sentinel
+        for chunk in (128, 4096, 40960, 0):
+            for nd, okind, oval in ((NoData.none(ct), orc.ND_NONE, None), (NoData.default(ct), orc.ND_DEFAULT, None),
+                                    (NoData.new(ct, sentinel), orc.ND_VALUE, orc.value(int(ct), sentinel))):
+                got = raster_io.ingest(a, nd, masked=True, chunk_cells=chunk)
+                assert np.array_equal(got.buffer().to_vec().view(np.uint8), a.view(np.uint8))
+                want = orc.mask_from_nodata(a, okind, oval)
+                assert np.array_equal(got.mask().to_vec(), want), (ct, chunk, okind)
+                assert got.counts() == orc.mask_counts(want)
+        plain = raster_io.ingest(a, chunk_cells=1024)
+        assert plain == CellBuffer.from_vec(a)
+    assert raster_io.ingest(np.array([], dtype=np.int16), NoData.default(CellType.Int16), masked=True).len() == 0
+    # the streaming TIFF reader: strips of 7 rows, chunks that straddle strips, big-endian-free fixture layout
+    px = rng.integers(0, 65535, (301, 257)).astype(np.uint16)
+    px[rng.random(px.shape) < 0.01] = 0
+    p = str(tmp_path / "band.tiff")
+    raster_io.write_tiff(p, px, nodata=0.0, rows_per_strip=7)
+    whole, nd = raster_io.read_tiff(p)
+    m = raster_io.read_cells_masked(p, chunk_cells=1024)
+    assert np.array_equal(m.buffer().to_vec(), whole.reshape(-1)) and m.counts() == (int((px != 0).sum()), int((px == 0).sum()))
+    assert raster_io.read_cells(p, wait=True) == CellBuffer.from_vec(px.reshape(-1))

@@ -181,6 +181,14 @@ wn = orc.tight_binary(orc.DIV, orc.tight_binary(orc.SUB, nir_h, red_h), orc.tigh
 same(got, wn, "lazy NDVI")
 same(nir.normalized_difference(red).to_vec(), wn, "fused NDVI")
 
+# ---- chunked ingest: chunks go to the GPU that owns their strip; result identical to the one-shot upload -------------------------------
+from erased_cells_b200 import raster_io
+ing = raster_io.ingest(i1_h, nd, masked=True, chunk_cells=4096)
+assert ing.buffer().shard_count() == G and ec.lib().ec_mask_shard_count(ing.mask()._h) == G
+same(ing.buffer().to_vec(), i1_h, "sharded ingest data")
+assert np.array_equal(ing.mask().to_vec(), wm1) and ing.counts() == orc.mask_counts(wm1)
+assert raster_io.ingest(a_h, chunk_cells=1000) == a
+
 # ---- strips that come out empty (fewer than 128 cells per strip): every strip keeps the raster's cell type -------------------------
 ec.set_shard_min_cells(1)
 t_h = cells(CellType.Float32, 100, 9)
