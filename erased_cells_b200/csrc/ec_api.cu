@@ -823,34 +823,45 @@ struct JitBuild {
     int ops = 0;
     bool ok = true;
 };
-static std::string jit_gen(JitBuild& b, Expr& e);
-static std::string jit_value(JitBuild& b, Operand& o) {
+// A generated sub-expression and, when it is integer-typed, a bound on its magnitude in bits: integer cells (8..64) and
+// sums / differences of integer-typed values (one more bit each). Such values are 0 or lie in [1, 2^bits], never -0
+// (a product could be: 0 * -3), never NaN / infinite — the domain of the guard-free quotient (ecj_divi). -1: anything else.
+struct JitTerm {
+    std::string s;
+    int int_bits;
+};
+static JitTerm jit_gen(JitBuild& b, Expr& e);
+static JitTerm jit_value(JitBuild& b, Operand& o) {
     if (inlineable(o)) return jit_gen(b, *o.expr);
     int k = 0;
     for (; k < b.p.n_in; ++k)
         if (b.p.in[k] == o.ptr && b.p.ct[k] == o.ct) break;
     if (k == b.p.n_in) {
-        if (k == kJitInputs) { b.ok = false; return "v0"; }
+        if (k == kJitInputs) { b.ok = false; return {"v0", -1}; }
         use_block(o.blk.get());
         b.p.in[k] = o.ptr;
         b.p.ct[k] = o.ct;
         ++b.p.n_in;
     }
-    return "v" + std::to_string(k);
+    return {"v" + std::to_string(k), ct_integral(o.ct) ? int(kSize[o.ct]) * 8 : -1};
 }
-static std::string jit_gen(JitBuild& b, Expr& e) {
+static JitTerm jit_gen(JitBuild& b, Expr& e) {
     static const char* const fn[4] = {"ecj_add", "ecj_sub", "ecj_mul", "ecj_div"};
-    if (!b.ok || ++b.ops > kJitOps) { b.ok = false; return "v0"; }
-    const std::string l = jit_value(b, e.l);
-    std::string r;
+    if (!b.ok || ++b.ops > kJitOps) { b.ok = false; return {"v0", -1}; }
+    const JitTerm l = jit_value(b, e.l);
+    JitTerm r{"", -1};
     if (e.kind == EX_SCALAR) {  // scalars are kernel parameters: one binary serves every value
-        if (b.p.n_const == kJitConsts) { b.ok = false; return "v0"; }
+        if (b.p.n_const == kJitConsts) { b.ok = false; return {"v0", -1}; }
         b.p.consts[b.p.n_const] = e.s;
-        r = "c" + std::to_string(b.p.n_const++);
+        r.s = "c" + std::to_string(b.p.n_const++);
     } else {
         r = jit_value(b, e.r);
     }
-    return std::string(fn[e.op & 3]) + "(" + l + ", " + r + ")";
+    const int op = e.op & 3;
+    const bool ints = l.int_bits > 0 && r.int_bits > 0;
+    const char* f = (op == EC_DIV && ints && std::max(l.int_bits, r.int_bits) <= 65) ? "ecj_divi" : fn[op];
+    const int bits = (ints && (op == EC_ADD || op == EC_SUB) && std::max(l.int_bits, r.int_bits) < 65) ? std::max(l.int_bits, r.int_bits) + 1 : -1;
+    return {std::string(f) + "(" + l.s + ", " + r.s + ")", bits};
 }
 
 static ec_status eval_operand(Operand& o) {
@@ -888,7 +899,7 @@ static ec_status eval(Expr& e) {
     } else if (t_lazy == 3 && fusable_ops(e) >= 2 && [&] {  // opt-in: a longer chain as ONE kernel specialised at run time (ec_jit.cu)
                    if (jit_prepare(e) != EC_OK) return false;
                    JitBuild b;
-                   b.p.expr = jit_gen(b, e);
+                   b.p.expr = jit_gen(b, e).s;
                    if (!b.ok) return false;
                    if (launch_jit(launch_ctx(), b.p, static_cast<double*>(out), e.n, &err) != 0) return false;  // no NVRTC here: op by op
                    family = "expression_jit(lazy)";

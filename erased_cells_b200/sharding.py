@@ -170,6 +170,18 @@ class Comm:
             self._h = None
 
 
+_NEG_OUT = {CellType.UInt8: CellType.Int16, CellType.UInt16: CellType.Int32, CellType.UInt32: CellType.Float64, CellType.UInt64: CellType.Float64}
+
+
+def _typed(strip: CellBuffer, ct: CellType) -> CellBuffer:
+    """An op on an EMPTY strip returns UInt8([]) (FromIterator of nothing, src/buffer.rs:233-236) — right for an empty raster,
+    wrong for the empty strip of a non-empty one (fewer rows than ranks): the other ranks hold Float64, and a reduction would
+    mix UInt8 seed keys with Float64 keys. The strip keeps the raster's logical cell type instead."""
+    if strip.len() == 0 and strip.cell_type() != ct:
+        return CellBuffer.with_defaults(0, ct)
+    return strip
+
+
 class ShardedCellBuffer:
     """One raster, row-strip sharded over the ranks of a Comm: this rank holds `strip` (rows
     [row0, row0 + rows)). Element-wise ops, neg and convert are shard-local and return another ShardedCellBuffer;
@@ -187,8 +199,8 @@ class ShardedCellBuffer:
         off, ln = row_strip(w, h, comm.n_ranks, comm.rank)
         return ShardedCellBuffer(CellBuffer.from_vec(raster.reshape(-1)[off:off + ln]), w, h, comm)
 
-    def _like(self, strip):
-        return type(self)(strip, self.width, self.height, self.comm)
+    def _like(self, strip, ct: CellType):
+        return type(self)(_typed(strip, ct) if self.len() else strip, self.width, self.height, self.comm)
 
     def len(self) -> int:
         return self.width * self.height
@@ -197,16 +209,16 @@ class ShardedCellBuffer:
         return self.strip.cell_type()
 
     def _bin(self, op, rhs):
-        return self._like(self.strip._bin(op, rhs.strip if isinstance(rhs, ShardedCellBuffer) else rhs))
+        return self._like(self.strip._bin(op, rhs.strip if isinstance(rhs, ShardedCellBuffer) else rhs), CellType.Float64)
 
     def __add__(self, r): return self._bin(0, r)
     def __sub__(self, r): return self._bin(1, r)
     def __mul__(self, r): return self._bin(2, r)
     def __truediv__(self, r): return self._bin(3, r)
-    def __neg__(self): return self._like(-self.strip)
+    def __neg__(self): return self._like(-self.strip, _NEG_OUT.get(self.cell_type(), self.cell_type()))
 
     def convert(self, ct: CellType):
-        return self._like(self.strip.convert(ct))
+        return self._like(self.strip.convert(ct), ct)
 
     def min_max(self):
         return self.comm.min_max(self.strip)
@@ -237,8 +249,11 @@ class ShardedMaskedCellBuffer:
         return ShardedMaskedCellBuffer(MaskedCellBuffer.from_buffer_with_nodata(buf, nodata), w, h, comm)
 
     def _bin(self, op, rhs):
-        return ShardedMaskedCellBuffer(self.strip._bin(op, rhs.strip if isinstance(rhs, ShardedMaskedCellBuffer) else rhs),
-                                       self.width, self.height, self.comm)
+        from .api import MaskedCellBuffer
+        r = self.strip._bin(op, rhs.strip if isinstance(rhs, ShardedMaskedCellBuffer) else rhs)
+        if self.width * self.height:
+            r = MaskedCellBuffer(_typed(r.buffer(), CellType.Float64), r.mask())
+        return ShardedMaskedCellBuffer(r, self.width, self.height, self.comm)
 
     def __add__(self, r): return self._bin(0, r)
     def __sub__(self, r): return self._bin(1, r)

@@ -57,6 +57,15 @@ inline void check(ec_status s) {
 }
 }  // namespace detail
 
+// ---- one process, several GPUs (extension; the crate is single-threaded CPU code) -------------------------------------
+// Call before the first buffer is made (or set EC_DEVICES=0,1,...): from then on buffers / masks of at least
+// set_shard_min_cells() cells live as row strips, one per GPU, behind the very same CellBuffer / Mask objects.
+inline int init_devices(const std::vector<int>& devices) {
+    detail::check(ec_init_devices(devices.data(), static_cast<int>(devices.size())));
+    return ec_device_count();
+}
+inline size_t set_shard_min_cells(size_t cells) { return ec_set_shard_min_cells(cells); }
+
 // ---- CellEncoding — src/encoding.rs:9-40 ----------------------------------------------------------
 template <class T> struct CellEncoding;  // only the ten primitives are CellEncoding
 #define EC_HPP_WITH_CT(X) \
@@ -198,6 +207,9 @@ public:
     size_t len() const { return ec_buf_len(h_); }
     bool is_empty() const { return len() == 0; }
     CellType cell_type() const { return CellType(ec_buf_ctype(h_)); }
+    // row strips this buffer is kept as (0: one GPU) and where strip g lives
+    int shard_count() const { return ec_buf_shard_count(h_); }
+    ec_shard_info shard(int g) const { ec_shard_info i; detail::check(ec_buf_shard(h_, g, &i, nullptr)); return i; }
     // cells [offset, offset + len) as a buffer sharing this allocation (a row strip; offset on a 32-byte boundary)
     CellBuffer view(size_t offset, size_t len) const { ec_buf* h; detail::check(ec_buf_view(h_, offset, len, &h)); return own(h); }
     CellValue get(size_t index) const { CellValue o; detail::check(ec_buf_get(h_, index, &o.v)); return o; }

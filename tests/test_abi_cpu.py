@@ -169,6 +169,9 @@ def test_jit_kernels_build_for_sm100a_without_a_gpu():
         cts = (C.c_uint8 * 2)(ct, 9 - ct)
         assert L.ec_jit_dry_build(cts, 2, 1, b"ecj_mul(ecj_add(v0, v1), c0)", log, len(log)) == _lib.EC_OK, log.value.decode()
     cts = (C.c_uint8 * 8)(*([9] * 8))
+    # integer-typed sub-expressions take the guard-free quotient (ecj_divi): (v0 - v1) / (v0 + v1) * c0 over u16 cells
+    cts2 = (C.c_uint8 * 2)(1, 1)
+    assert L.ec_jit_dry_build(cts2, 2, 1, b"ecj_mul(ecj_divi(ecj_sub(v0, v1), ecj_add(v0, v1)), c0)", log, len(log)) == _lib.EC_OK, log.value.decode()
     expr = b"ecj_add(ecj_add(ecj_add(v0, v1), ecj_add(v2, v3)), ecj_add(ecj_add(v4, v5), ecj_add(v6, v7)))"
     assert L.ec_jit_dry_build(cts, 8, 0, expr, log, len(log)) == _lib.EC_OK, log.value.decode()
     assert L.ec_jit_dry_build(cts, 2, 0, b"not_a_function(v0, v1)", log, len(log)) == _lib.EC_INVALID_ARG and b"not_a_function" in log.value

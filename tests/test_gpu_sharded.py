@@ -55,3 +55,13 @@ def test_reference_test_suites_on_sharded_handles():
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", os.path.join(ROOT, "tests", "test_gpu_reference_kat.py")],
                        capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+def test_cpp_drives_two_strips_in_one_process():
+    """tests/cpp/test_sharded.cpp: the sharded handles through the C++ mirror, CUDA device 0 listed twice"""
+    exe = os.path.join(ROOT, "tests", "cpp", "build", "test_sharded")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "-s"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and " 0 failed" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

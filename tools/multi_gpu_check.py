@@ -91,6 +91,24 @@ if rank == 0:
     print(f"ShardedCellBuffer / ShardedMaskedCellBuffer NDVI (1031 x 512, ragged strips) == single GPU: {good}, counts {sharded_counts}")
 ok &= good
 
+# fewer rows than ranks (the first strips are empty): every rank still takes part with the raster's cell type
+tiny_h = rng.random((1, 256)).astype(np.float32)  # one row: only the last rank holds cells
+ts = sharding.ShardedCellBuffer.from_host(tiny_h, comm_obj)
+tr = (ts * 2.0 - ts) / 3.0
+assert tr.strip.cell_type() == CellType.Float64, tr.strip.cell_type()
+one_t = (CellBuffer.from_vec(tiny_h.reshape(-1)) * 2.0 - CellBuffer.from_vec(tiny_h.reshape(-1))) / 3.0
+good = tuple(v.bits for v in tr.min_max()) == tuple(v.bits for v in one_t.min_max())
+good &= same_stats(tr.statistics(), one_t.statistics())
+good &= tuple(v.bits for v in (-ts).min_max()) == tuple(v.bits for v in (-CellBuffer.from_vec(tiny_h.reshape(-1))).min_max())
+tm = sharding.ShardedMaskedCellBuffer.from_host_with_nodata(tiny_h, NoData.new(CellType.Float32, float(tiny_h[0, 3])), comm_obj)
+tmr = (tm + tm) * 0.5
+tm_one = MaskedCellBuffer.from_vec_with_nodata(tiny_h.reshape(-1), NoData.new(CellType.Float32, float(tiny_h[0, 3])))
+tm_one = (tm_one + tm_one) * 0.5
+good &= tmr.counts() == tm_one.counts() and tuple(v.bits for v in tmr.min_max()) == tuple(v.bits for v in tm_one.min_max())
+if rank == 0:
+    print(f"one-row raster over {world} ranks (empty strips keep the logical cell type): {good}")
+ok &= good
+
 # latency of the two ways to finish a sharded f32 min_max (device events around 50 calls)
 strip = synth.device(CellType.Float32, ln, 0xEC40, index_offset=off, kind=synth.REAL_RANGE, lo=-1e4, hi=1e4)
 for label, fn in (("torch.distributed NCCL all-reduce", lambda: sharding.min_max_sharded(strip)), ("ec_comm (peer exchange in the kernel)" if comm_obj.peer_exchange else "ec_comm (NCCL)", lambda: comm_obj.min_max(strip))):
