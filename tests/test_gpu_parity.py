@@ -161,6 +161,48 @@ def test_mask_ops(orc):
     assert Mask.new([False, True]) < Mask.new([True, False]) and Mask.new([True]) < Mask.new([True, False])
 
 
+def test_mask_counts_follow_mutation(orc):
+    """Mask::counts (src/masked/mask.rs:72-80) comes with the mask: the kernel that wrote it counted its set bits. The
+    cached count must follow every way a mask can change (put, extend, copy on write of shared words) and never be
+    served for different bits; masked scalar / neg results share the operand's mask words instead of copying them."""
+    L = ec.lib()
+    n = 3 * 32768 + 41
+    a = synth.host(CellType.Int16, n, 0xC01, kind=synth.INT_RANGE, lo=-32768, hi=32767, period=20, sentinel=-32768)
+    b = synth.host(CellType.Int16, n, 0xC02, kind=synth.INT_RANGE, lo=-32768, hi=32767, period=30, sentinel=-32768)
+    nd = NoData.default(CellType.Int16)
+    ma, mb = MaskedCellBuffer.from_vec_with_nodata(a, nd), MaskedCellBuffer.from_vec_with_nodata(b, nd)
+    wa, wb = orc.mask_from_nodata(a, orc.ND_DEFAULT), orc.mask_from_nodata(b, orc.ND_DEFAULT)
+    k0 = L.ec_kernel_launches()
+    assert ma.counts() == orc.mask_counts(wa) and mb.counts() == orc.mask_counts(wb)
+    r = ma - mb
+    assert r.counts() == orc.mask_counts(orc.mask_and(wa, wb))
+    assert (ma.mask() | mb.mask()).counts() == orc.mask_counts(orc.mask_or(wa, wb))
+    assert (~ma.mask()).counts() == orc.mask_counts(orc.mask_not(wa))
+    assert ma.mask().slice(32768, 40000).counts() == orc.mask_counts(wa[32768:72768])
+    # none of those counts needed a popcount launch: 1 masked binary + 1 or + 1 not + 1 slice
+    assert L.ec_kernel_launches() == k0 + 4, L.ec_kernel_launches() - k0
+    # masked * scalar and -masked: the mask words are shared, not copied
+    s, g = r * 0.5, -ma
+    assert L.ec_mask_device_words(s.mask()._h) == L.ec_mask_device_words(r.mask()._h)
+    assert L.ec_mask_device_words(g.mask()._h) == L.ec_mask_device_words(ma.mask()._h)
+    assert s.counts() == r.counts() and g.counts() == ma.counts()
+    # put on one of the sharers copies first; the cached counts follow the mutation, the other side keeps its bits
+    before = r.counts()
+    i = int(np.flatnonzero(orc.mask_and(wa, wb))[7])
+    s.mask_mut().put(i, False)
+    assert s.counts() == (before[0] - 1, before[1] + 1) and r.counts() == before
+    assert L.ec_mask_device_words(s.mask()._h) != L.ec_mask_device_words(r.mask()._h)
+    assert r.mask().get(i) and not s.mask().get(i)
+    s.mask_mut().put(i, False)  # no change: count stays
+    assert s.counts() == (before[0] - 1, before[1] + 1)
+    s.mask_mut().put(i, True)
+    assert s.counts() == before and s.mask() == r.mask()
+    m = Mask.new(wa)
+    m.extend([True, True, False])
+    assert m.counts() == (orc.mask_counts(wa)[0] + 2, orc.mask_counts(wa)[1] + 1)
+    assert m.counts() == orc.mask_counts(m.to_vec())
+
+
 def test_from_nodata_and_fill_nodata(orc):
     for ct in CT:
         for n in (0, 5, 4096 + 33, 65536 + 7):

@@ -40,7 +40,8 @@ def launches(path, cells):
         t = r.get("gpu__time_duration.sum", 0) / 1e3
         rd, wr = r.get("dram__bytes_read.sum", 0) / 1e6, r.get("dram__bytes_write.sum", 0) / 1e6
         cb = cast_bytes(r["name"])
-        alg = (cb[0] + cb[1]) * cells / 1e6 if cb and cb[0] and cb[1] else None
+        small = int(re.sub(r"[^0-9,]", "", r["grid"]).split(",")[0] or 0) < 256  # a parity-check window, not a full buffer
+        alg = (cb[0] + cb[1]) * cells / 1e6 if cb and cb[0] and cb[1] and not small else None
         fam = short(r["name"]).split("<")[0]
         tot[fam + "_us"] += t
         tot[fam + "_n"] += 1
