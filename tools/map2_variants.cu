@@ -44,6 +44,48 @@ __global__ void __launch_bounds__(THREADS, MINCTAS) variant_kernel(const typenam
         for (size_t i = full * TILE + threadIdx.x; i < n; i += THREADS) o[i] = f(a[i], b[i]);
 }
 
+// BAL: a persistent grid of exactly the resident CTAs (MINCTAS per SM), every CTA streaming one contiguous range of
+// 1024-cell mini tiles, balanced to +-1 mini tile: all CTAs start together and end together (no partial last wave).
+template <class F, int UNROLL, int THREADS, int MINCTAS>
+__global__ void __launch_bounds__(THREADS, MINCTAS) balanced_kernel(const typename F::A* __restrict__ a, const typename F::B* __restrict__ b,
+                                                                    double* __restrict__ o, size_t n, F f) {
+    using A = typename F::A; using B = typename F::B;
+    constexpr int V = 4;
+    constexpr size_t MT = size_t(THREADS) * V;
+    const size_t mts = n / MT;
+    const size_t lo = size_t(blockIdx.x) * mts / gridDim.x, hi = size_t(blockIdx.x + 1) * mts / gridDim.x;
+    overlap_prologue();
+    size_t t = lo;
+    for (; t + UNROLL <= hi; t += UNROLL) {
+        const size_t base = t * MT + size_t(threadIdx.x) * V;
+        Vec<A, V> va[UNROLL];
+        Vec<B, V> vb[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            va[u] = ld_stream<A, V>(a + base + size_t(u) * MT);
+            vb[u] = ld_stream<B, V>(b + base + size_t(u) * MT);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            Vec<double, V> vo;
+#pragma unroll
+            for (int j = 0; j < V; ++j) vo.v[j] = f(va[u].v[j], vb[u].v[j]);
+            st_stream<double, V>(o + base + size_t(u) * MT, vo);
+        }
+    }
+    for (; t < hi; ++t) {
+        const size_t base = t * MT + size_t(threadIdx.x) * V;
+        const Vec<A, V> va = ld_stream<A, V>(a + base);
+        const Vec<B, V> vb = ld_stream<B, V>(b + base);
+        Vec<double, V> vo;
+#pragma unroll
+        for (int j = 0; j < V; ++j) vo.v[j] = f(va.v[j], vb.v[j]);
+        st_stream<double, V>(o + base, vo);
+    }
+    if (blockIdx.x == gridDim.x - 1)
+        for (size_t i = mts * MT + threadIdx.x; i < n; i += THREADS) o[i] = f(a[i], b[i]);
+}
+
 static cudaEvent_t e0, e1;
 static unsigned g_it = 0;
 template <class Launch> static float timed(Launch&& go, int iters) {
@@ -67,6 +109,11 @@ static float run_variant(const typename F::A* a, const typename F::B* b, double*
     const int grid = int(n / TILE ? n / TILE : 1);
     return timed([&] { const size_t s = (g_it++ % slots) * n; variant_kernel<F, UNROLL, THREADS, MINCTAS, SEQ><<<grid, THREADS>>>(a + s, b + s, o + s, n, F{}); }, iters);
 }
+template <class F, int UNROLL, int MINCTAS>
+static float run_balanced(const typename F::A* a, const typename F::B* b, double* o, size_t n, size_t slots, int iters, int sms) {
+    const int grid = sms * MINCTAS;
+    return timed([&] { const size_t s = (g_it++ % slots) * n; balanced_kernel<F, UNROLL, 256, MINCTAS><<<grid, 256>>>(a + s, b + s, o + s, n, F{}); }, iters);
+}
 template <class F> static float run_lib(const typename F::A* a, const typename F::B* b, double* o, size_t n, size_t slots, int iters) {
     constexpr size_t TILE = size_t(256) * 4 * 4;
     const int grid = int(n / TILE ? n / TILE : 1);
@@ -84,9 +131,12 @@ template <class F> static void sweep(const char* name, const typename F::A* a, c
                            run_variant<F, 2, 128, 8, false>(a, b, o, n, slots, iters),
                            run_variant<F, 8, 256, 4, false>(a, b, o, n, slots, iters),
                            run_variant<F, 4, 256, 4, false>(a, b, o, n, slots, iters),
-                           run_variant<F, 2, 256, 4, true>(a, b, o, n, slots, iters)};
-        printf("%s n=2^%d us:  LIB %.2f  SEQ %.2f  R80 %.2f  R80SEQ %.2f  U2 %.2f  U2T128 %.2f  U8 %.2f  PLAIN(U4,64r) %.2f  U2SEQ %.2f   (ideal at 6.53 TB/s: %.2f)\n", name,
-               63 - __builtin_clzll(n), t[0] * 1e3, t[1] * 1e3, t[2] * 1e3, t[3] * 1e3, t[4] * 1e3, t[5] * 1e3, t[6] * 1e3, t[7] * 1e3, t[8] * 1e3, bpc * n / 6532.5e9 * 1e6);
+                           run_variant<F, 2, 256, 4, true>(a, b, o, n, slots, iters),
+                           run_balanced<F, 4, 4>(a, b, o, n, slots, iters, 148), run_balanced<F, 8, 4>(a, b, o, n, slots, iters, 148),
+                           run_balanced<F, 2, 4>(a, b, o, n, slots, iters, 148), run_balanced<F, 4, 3>(a, b, o, n, slots, iters, 148)};
+        printf("%s n=2^%d us:  LIB %.2f  SEQ %.2f  R80 %.2f  R80SEQ %.2f  U2 %.2f  U2T128 %.2f  U8 %.2f  PLAIN(U4,64r) %.2f  U2SEQ %.2f  BAL_U4 %.2f  BAL_U8 %.2f  BAL_U2 %.2f  BAL_U4_3cta %.2f   (ideal at 6.53 TB/s: %.2f)\n", name,
+               63 - __builtin_clzll(n), t[0] * 1e3, t[1] * 1e3, t[2] * 1e3, t[3] * 1e3, t[4] * 1e3, t[5] * 1e3, t[6] * 1e3, t[7] * 1e3, t[8] * 1e3, t[9] * 1e3, t[10] * 1e3, t[11] * 1e3, t[12] * 1e3,
+               bpc * n / 6532.5e9 * 1e6);
     }
 }
 __global__ void fill(uint8_t* p, size_t n, uint64_t seed) {
