@@ -1,6 +1,8 @@
 """Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
 Bit-exact for everything: integer, cast, mask and f64 work (NaN results follow the x86 rule the
 reference's platform produces). Run on the B200 box: pytest -m gpu."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -778,3 +780,67 @@ def test_special_value_cross_product_all_ops_and_fused(orc):
                 assert np.array_equal(bits(got), bits(orc.tight_scalar(op2, want, orc.value(orc.Float64, s)))), (lct, rct, op, op2, s)
         nd = orc.tight_binary(orc.DIV, orc.tight_binary(orc.SUB, l, r), orc.tight_binary(orc.ADD, l, r))
         assert np.array_equal(bits(dl.normalized_difference(dr).to_vec()), bits(nd)), (lct, rct)
+
+
+def test_handles_cross_streams_and_threads(orc):
+    """Handles are Send + Sync for real: a buffer produced on one thread's stream is read, combined and dropped on other
+    threads that each enqueue on a stream of their own (ec_set_stream). The allocator orders a foreign stream against the
+    block's home stream on first touch and does not recycle the block before every such stream has passed it — so a
+    heavy producer followed at once by consumers elsewhere, and blocks freed on the "wrong" thread and reused right away,
+    must still give the oracle's bits."""
+    import threading
+
+    import torch
+    L = ec.lib()
+    n = 6 * 1024 * 1024 + 17
+    a_h, b_h = cells(CellType.UInt16, n, 0xD01), cells(CellType.Int16, n, 0xD02)
+    a, b = CellBuffer.from_vec(a_h), CellBuffer.from_vec(b_h)
+    want_sum = orc.tight_binary(orc.ADD, a_h, b_h)
+    want = orc.tight_scalar(orc.MUL, want_sum, orc.value(orc.Float64, 0.5))
+    errors = []
+
+    def consumer(k, produced, out):
+        try:
+            s = torch.cuda.Stream()
+            ec._lib.check(L.ec_set_stream(C.c_void_p(s.cuda_stream)))
+            for rep in range(6):
+                r = produced[rep] * 0.5                      # reads a block whose producer ran on the main thread's stream
+                got = r.to_vec()
+                if not np.array_equal(bits(got), bits(want)):
+                    errors.append((k, rep, "wrong bits"))
+                produced[rep] = None if k == 0 else produced[rep]   # thread 0 drops the handles: freed on a foreign thread
+                del r
+            ec._lib.check(L.ec_set_stream(None))
+        except Exception as e:  # noqa: BLE001
+            errors.append((k, repr(e)))
+
+    for round_ in range(3):
+        produced = [a + b for _ in range(6)]                 # queued back to back on the main stream, not waited for
+        ts = [threading.Thread(target=consumer, args=(k, list(produced) if k else produced, None)) for k in range(3)]
+        [t.start() for t in ts]
+        churn = [(a - b) for _ in range(6)]                  # meanwhile the main stream recycles blocks of the same size
+        [t.join() for t in ts]
+        del churn, produced
+        assert (a + b) == CellBuffer.from_vec(want_sum)
+    assert not errors, errors[:5]
+
+
+def test_views_alias_their_parent(orc):
+    """ec_buf_view shares the allocation: a put through a view is seen by the parent and the other way round (views are
+    aliases, pending lazy operands are snapshots); nothing about the cells is cached while a view lives."""
+    h = synth.host(CellType.Float32, 4096, 0xD10, kind=synth.REAL_RANGE, lo=-5.0, hi=5.0)
+    p = CellBuffer.from_vec(h)
+    mn0, mx0 = p.min_max()
+    v = p.view(1024, 512)
+    v.put(3, np.float32(99.0))
+    assert p.get(1027).value() == np.float32(99.0)
+    assert p.min_max()[1].value() == np.float32(99.0)        # not the value remembered before the view existed
+    p.put(1030, np.float32(-77.0))
+    assert v.get(6).value() == np.float32(-77.0) and v.min_max()[0].value() == np.float32(-77.0)
+    with ec.lazy():
+        pending = p * 2.0                                    # a snapshot: later puts must not change it
+        p.put(0, np.float32(1234.0))
+        first = pending.get(0).value()
+    assert first == np.float64(h[0]) * 2.0
+    del v
+    assert p.min_max()[1].value() == np.float32(1234.0)
