@@ -422,11 +422,11 @@ static ec_status poll_tag(volatile uint64_t* tag_word, uint64_t tag, cudaStream_
     }
 }
 // wait until all five words of a published result carry the call's tag (see block_finish in ec_reduce.cuh)
-static ec_status poll_result(const PendingReduce& p) {
+static ec_status poll_result(const PendingReduce& p, int words = 5) {
     const uint64_t tag = p.seq << 32;
     for (unsigned long spins = 0;; ++spins) {
         bool all = true;
-        for (int i = 0; i < 5; ++i) all = all && ((p.pin[i] ^ tag) >> 32) == 0;
+        for (int i = 0; i < words; ++i) all = all && ((p.pin[i] ^ tag) >> 32) == 0;
         if (all) { std::atomic_thread_fence(std::memory_order_acquire); return EC_OK; }
 #if defined(__x86_64__)
         __builtin_ia32_pause();
@@ -436,7 +436,7 @@ static ec_status poll_result(const PendingReduce& p) {
             const cudaError_t q = cudaStreamQuery(p.stream);
             if (q == cudaSuccess) {
                 all = true;
-                for (int i = 0; i < 5; ++i) all = all && ((p.pin[i] ^ tag) >> 32) == 0;
+                for (int i = 0; i < words; ++i) all = all && ((p.pin[i] ^ tag) >> 32) == 0;
                 if (all) return EC_OK;
                 set_error("a reduction kernel finished without publishing its result");
                 return EC_CUDA;
@@ -1063,6 +1063,33 @@ ec_status moments_begin(const ec_buf* b, const ec_mask* m, double pivot, int exp
     EC_LAUNCH(launch_moments(launch_ctx(), b->ct, rd(b), m ? rdm(m) : nullptr, b->len, pivot, std::ldexp(1.0, -exp2),
                              static_cast<unsigned long long*>(acc.p)), "moments");
     EC_CUDA_TRY(cudaMemcpyAsync(p->pin, acc.p, EC_MOMENT_WORDS * sizeof(uint64_t), cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
+    return EC_OK;
+}
+ec_status moments_exchange(const ec_buf* b, const ec_mask* m, double pivot, int exp2, const PeerExchange& px, unsigned long long region_off,
+                           uint64_t* total) {
+    EC_TRY(ensure());
+    EC_TRY(resolve(b));
+    const bool quant = b->ct == EC_FLOAT32, ints = stats_integer_route(b->ct) || quant;
+    const int K = ints ? 5 : EC_MOMENT_WORDS, pairs = ints ? 2 : 4;
+    Scratch acc;  // released at return: reuse of the block is ordered after the exchange kernel by stream order
+    EC_TRY(acc.alloc(EC_MOMENT_WORDS * sizeof(uint64_t)));
+    if (ints) EC_CUDA_TRY(cudaMemcpyAsync(acc.p, kIntStatsInit, sizeof kIntStatsInit, cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
+    else EC_CUDA_TRY(cudaMemsetAsync(acc.p, 0, EC_MOMENT_WORDS * sizeof(uint64_t), cur_stream()), "cudaMemsetAsync");
+    unsigned long long* dacc = static_cast<unsigned long long*>(acc.p);
+    if (b->len) {  // an empty strip still takes part in the exchange, with all-zero sums
+        if (quant) EC_LAUNCH(launch_quant_stats(launch_ctx(), rd(b), m ? rdm(m) : nullptr, b->len, dacc, exp2), "quant_stats");
+        else if (ints) EC_LAUNCH(launch_int_stats(launch_ctx(), b->ct, rd(b), m ? rdm(m) : nullptr, b->len, dacc), "int_stats");
+        else EC_LAUNCH(launch_moments(launch_ctx(), b->ct, rd(b), m ? rdm(m) : nullptr, b->len, pivot, std::ldexp(1.0, -exp2), dacc), "moments");
+    }
+    uint64_t* pin;
+    EC_TRY(pinned_words(&pin));
+    ThreadDev& td = t_td[t_dev];
+    PendingReduce pend{td.pinned + 40, 0x80000000ull | (++td.seq & 0x7FFFFFFFull), cur_stream(), t_dev};
+    EC_LAUNCH(launch_exchange_sums(launch_ctx(), dacc, K, pairs, px, region_off, td.pinned_dev + 40, pend.seq), "statistics_sums(peer exchange)");
+    EC_TRY(poll_result(pend, 2 * K + 1));
+    memset(total, 0, EC_MOMENT_WORDS * sizeof(uint64_t));
+    for (int k = 0; k < K; ++k) total[k] = (pend.pin[2 * k] & 0xFFFFFFFFull) | (pend.pin[2 * k + 1] << 32);
+    if ((pend.pin[2 * K] & 0xFFFFFFFFull) != 0) { set_error("a peer GPU did not deliver its statistics sums within the spin limit"); return EC_NCCL; }
     return EC_OK;
 }
 ec_status stats_end(const StatsPending& p, uint64_t* w) {

@@ -114,7 +114,8 @@ static ec_status peer_setup(ec_comm* c) {
     c->peer_ok = false;
     if (c->n_ranks > 32 || env_int("EC_NO_PEER_EXCHANGE", 0)) return EC_OK;  // one warp folds the ranks; NCCL path otherwise (same decision on every rank)
     cudaStream_t st = static_cast<cudaStream_t>(ec_get_stream());
-    const size_t words = size_t(2) * c->n_ranks * 4;
+    // two regions: the 4-word min_max / counts messages, then the 20-word statistics-sums messages (2 epochs x n_ranks slots each)
+    const size_t words = size_t(2) * c->n_ranks * 4 + size_t(2) * c->n_ranks * 2 * kSumWords;
     int ok = 1;
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof mine);
@@ -268,6 +269,12 @@ ec_status ec_buf_statistics_sharded(ec_comm* c, const ec_buf* shard, const ec_ma
     double p;
     if (ec_status s = ec_statistics_plan(&mn, &mx, &kind, &p, &e)) return s;
     uint64_t raw[EC_MOMENT_WORDS] = {0};
+    if (kind == EC_STATS_REGULAR && c->peer_ok) {
+        // the sums ride the peer mailboxes like the min_max keys: statistics kernel + one exchanging CTA behind it, no NCCL
+        uint64_t total[EC_MOMENT_WORDS];
+        if (ec_status s = moments_exchange(shard, mask_or_null, p, e, next_exchange(c), size_t(2) * c->n_ranks * 4, total)) return s;
+        return ec_statistics_finish(total, 1, &mn, &mx, out);
+    }
     if (kind == EC_STATS_REGULAR) {
         if (ec_status s = ec_buf_moments(shard, mask_or_null, p, e, raw)) return s;
     } else if (mask_or_null) {

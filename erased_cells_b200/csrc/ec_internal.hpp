@@ -234,6 +234,11 @@ int jit_dry_build(const JitProgram& p, std::string* source, std::string* log);
 cudaError_t launch_min_max(const Launch& L, int ct, const void* a, const uint32_t* mask, size_t n,
                            const ReduceScratch& s);
 cudaError_t launch_popcount(const Launch& L, const uint32_t* words, size_t nwords, const ReduceScratch& s, uint64_t second_word);
+cudaError_t launch_exchange_sums(const Launch& L, const unsigned long long* local, int words, int pairs, const PeerExchange& px,
+                                 unsigned long long region_off, uint64_t* host_words, uint64_t host_seq);
+// this strip's raw statistics sums, added exactly over all ranks inside one extra CTA behind the statistics kernel; total[9]
+ec_status moments_exchange(const ec_buf* b, const ec_mask* m, double pivot, int exp2, const PeerExchange& px, unsigned long long region_off,
+                           uint64_t* total);
 ec_status reduce_min_max_peer(const ec_buf* b, const ec_mask* m, const PeerExchange& px, uint64_t* k0, uint64_t* k1);
 ec_status reduce_popcount_peer(const ec_mask* m, const PeerExchange& px, uint64_t* ones, uint64_t* len_sum);
 // statistics extension: exact fixed-point moment sums into acc[9] (zeroed by the caller), see ec_stats.cuh

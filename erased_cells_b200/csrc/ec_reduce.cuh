@@ -178,6 +178,65 @@ __device__ __forceinline__ void block_finish(uint64_t k0, uint64_t k1, uint64_t 
     }
 }
 
+// ---- exact sums across the GPUs (statistics of a row-strip sharded raster) -----------------------------------------
+// After a strip's statistics kernel has left its raw accumulators in device memory — word 0 a plain count, then
+// `pairs` 128-bit two's complement sums as (lo, hi) words — ONE CTA sends them to every peer's mailbox, receives every
+// peer's, adds them exactly (carries included) and publishes the totals to mapped pinned host memory. Same
+// self-validating words as the min_max exchange: 32 payload bits under the epoch's tag, no fences. It is enqueued right
+// behind the statistics kernel, so its launch latency hides under that kernel.
+constexpr int kSumWords = 10;  // values per message (count + 4 pairs = 9 used)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) exchange_sums_kernel(const unsigned long long* __restrict__ local, int K, int pairs, PeerExchange px,
+                                                           unsigned long long region_off, uint64_t* host_words, uint64_t host_seq) {
+    __shared__ unsigned int half[32][2 * kSumWords];
+    __shared__ unsigned int status;
+    const int n = px.n_ranks, W = 2 * K;
+    const unsigned long long tag = (0x80000000ull | (px.epoch & 0x7FFFFFFFull)) << 32;
+    const unsigned long long slot_words = 2ull * kSumWords;
+    if (threadIdx.x == 0) status = 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * W; i += blockDim.x) {  // send: word w of my message into slot `rank` of peer r
+        const int r = i / W, w = i % W;
+        const unsigned long long v = local[w >> 1];
+        volatile unsigned long long* slot = px.peers[r] + region_off + ((px.epoch & 1ull) * n + px.rank) * slot_words + w;
+        *slot = tag | ((w & 1) ? (v >> 32) : (v & 0xFFFFFFFFull));
+    }
+    for (int i = threadIdx.x; i < n * W; i += blockDim.x) {  // receive: word w of rank r's message from my own mailbox
+        const int r = i / W, w = i % W;
+        volatile unsigned long long* slot = px.peers[px.rank] + region_off + ((px.epoch & 1ull) * n + r) * slot_words + w;
+        const long long t0 = clock64();
+        unsigned long long x;
+        for (;;) {
+            x = *slot;
+            if (((x ^ tag) >> 32) == 0) break;
+            if (static_cast<unsigned long long>(clock64() - t0) > px.spin_limit) { atomicOr(&status, 1u); x = 0; break; }
+        }
+        half[r][w] = static_cast<unsigned int>(x);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long tot[kSumWords];
+        for (int k = 0; k < K; ++k) tot[k] = 0;
+        for (int r = 0; r < n; ++r) {
+            tot[0] += (static_cast<unsigned long long>(half[r][1]) << 32) | half[r][0];
+            for (int p = 0; p < pairs; ++p) {  // 128-bit add with carry
+                const unsigned long long lo = (static_cast<unsigned long long>(half[r][2 * (1 + 2 * p) + 1]) << 32) | half[r][2 * (1 + 2 * p)];
+                const unsigned long long hi = (static_cast<unsigned long long>(half[r][2 * (2 + 2 * p) + 1]) << 32) | half[r][2 * (2 + 2 * p)];
+                const unsigned long long s = tot[1 + 2 * p] + lo;
+                tot[2 + 2 * p] += hi + (s < lo ? 1ull : 0ull);
+                tot[1 + 2 * p] = s;
+            }
+        }
+        volatile uint64_t* hr = host_words;
+        const uint64_t htag = host_seq << 32;
+        for (int k = 0; k < K; ++k) {
+            hr[2 * k] = htag | (tot[k] & 0xFFFFFFFFull);
+            hr[2 * k + 1] = htag | (tot[k] >> 32);
+        }
+        hr[W] = htag | status;
+    }
+}
+
 // ---- min_max ---------------------------------------------------------------------------------
 // Unmasked 8/16-bit cells are reduced two-at-a-time in packed 16-bit lanes (VIMNMX.U16x2); wider
 // cells and the masked flavour go cell by cell on 32/64-bit keys.

@@ -88,6 +88,12 @@ cudaError_t launch_popcount(const Launch& Lc, const uint32_t* words, size_t nwor
     return launch_k(Lc, popcount_kernel<kThreads>, grid, kThreads, words, nwords, s, second_word);
 }
 
+cudaError_t launch_exchange_sums(const Launch& Lc, const unsigned long long* local, int words, int pairs, const PeerExchange& px,
+                                 unsigned long long region_off, uint64_t* host_words, uint64_t host_seq) {
+    exchange_sums_kernel<256><<<1, 256, 0, Lc.stream>>>(local, words, pairs, px, region_off, host_words, host_seq);
+    return cudaGetLastError();
+}
+
 template <class U> static cudaError_t first_diff_u(const Launch& Lc, const void* a, const void* b, size_t n, const ReduceScratch& s) {
     const int grid = reduce_grid(n / (EC_VB / sizeof(U)), kThreads, Lc);
     return launch_k(Lc, first_diff_kernel<U, EC_VB, kThreads>, grid, kThreads, static_cast<const U*>(a), static_cast<const U*>(b), n, s);
