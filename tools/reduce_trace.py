@@ -42,7 +42,7 @@ for call in range(12):
     fn(*args)
     t = (C.c_uint64 * 12)()
     ec._lib.check(L.ec_reduce_trace_get(t))
-    v = np.array(list(t), dtype=np.int64)
+    v = np.array(list(t), dtype=np.uint64).view(np.int64).copy()
     v[3:9] = np.where(v[3:9] != 0, v[3:9] + v[9], 0)  # %globaltimer -> CLOCK_REALTIME axis
     rows.append(v[:9])
 # back-to-back calls (no barrier in between): what a loop of calls sees
@@ -51,7 +51,7 @@ for call in range(12):
     fn(*args)
     t = (C.c_uint64 * 12)()
     ec._lib.check(L.ec_reduce_trace_get(t))
-    v = np.array(list(t), dtype=np.int64)
+    v = np.array(list(t), dtype=np.uint64).view(np.int64).copy()
     v[3:9] = np.where(v[3:9] != 0, v[3:9] + v[9], 0)
     back.append(v[:9])
 L.ec_set_reduce_trace(0)
