@@ -36,6 +36,13 @@ def set_shard_min_cells(cells: int) -> int:
     return lib().ec_set_shard_min_cells(int(cells))
 
 
+def set_host_copy_threads(threads: int) -> int:
+    """Host threads that move a pageable array (numpy, a `Vec<T>`) to / from pinned staging while the DMA engine copies
+    the previous chunks (`ec_set_host_copy_threads`); 0 leaves pageable copies to the CUDA driver. Returns the previous
+    setting."""
+    return lib().ec_set_host_copy_threads(int(threads))
+
+
 def set_shard_finish(mode: int) -> int:
     """FINISH_HOST (host folds the strips' partials), FINISH_PEER (GPU-to-GPU exchange inside the reduction kernels) or
     FINISH_NCCL (ncclAllReduce); returns the previous mode"""
@@ -61,4 +68,4 @@ def lazy(on: bool = True, jit: bool = False):
 
 __all__ = ["CellBuffer", "CellType", "CellValue", "Mask", "MaskedCellBuffer", "NoData", "Statistics", "NarrowingError",
            "NoDeviceError", "EcError", "ParseError", "build", "lib", "lazy", "ADD", "SUB", "MUL", "DIV", "init_devices", "device_count", "set_shard_min_cells",
-           "set_shard_finish", "FINISH_HOST", "FINISH_PEER", "FINISH_NCCL"]
+           "set_host_copy_threads", "set_shard_finish", "FINISH_HOST", "FINISH_PEER", "FINISH_NCCL"]

@@ -147,6 +147,7 @@ def _signatures():
         "ec_ingest_submit": (S, [VP, SZ]),
         "ec_ingest_finish": (S, [VP, PVP, PVP]),
         "ec_ingest_abort": (None, [VP]),
+        "ec_set_host_copy_threads": (I, [I]),
         "ec_buf_with_defaults": (S, [SZ, U8, PVP]),
         "ec_buf_fill": (S, [SZ, PV, PVP]),
         "ec_buf_wrap_device": (S, [U8, VP, SZ, PVP]),

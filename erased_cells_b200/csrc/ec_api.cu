@@ -3,6 +3,9 @@
 // reference file:line each entry point replaces.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include <atomic>
 #include <cmath>
@@ -1532,19 +1535,28 @@ struct BufOwner {  // a half-built result: an early error return frees it
     ~BufOwner() { if (b) ec_buf_free(b); }
     ec_buf* release() { ec_buf* q = b; b = nullptr; return q; }
 };
+// a Vec<T> (pageable memory) into a fresh plain buffer, through the staging pipeline; the upload stream is ordered behind the
+// work still queued on the block (it may be recycled) and is drained before the call returns
+static ec_status staged_upload(ec_buf* b, const void* host) {
+    const cudaStream_t up = g_ctx.dev[t_dev].upload;
+    cudaEvent_t after = nullptr;
+    EC_CUDA_TRY(cudaEventCreateWithFlags(&after, cudaEventDisableTiming), "cudaEventCreate");
+    cudaError_t e = cudaEventRecord(after, cur_stream());
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(up, after, 0);
+    cudaEventDestroy(after);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
+    const HostSeg seg{t_dev, b->dptr, const_cast<void*>(host), b->len * kSize[b->ct], up};
+    return staged_transfer(&seg, 1, true);
+}
 ec_status ec_buf_from_host(uint8_t ct, const void* host, size_t len, ec_buf** out) {
     EC_TRY(ensure());
     if (!ct_ok(ct)) return invalid("cell type");
     if (shard_policy(len)) return sh_from_host(ct, host, len, false, out);
-    ec_buf* b;
-    EC_TRY(new_buf(ct, len, &b));
-    if (len) {
-        if (cudaError_t e = cudaMemcpyAsync(b->dptr, host, len * kSize[ct], cudaMemcpyHostToDevice, cur_stream())) {
-            ec_buf_free(b);
-            return cuda_fail(e, "cudaMemcpyAsync(H2D)");
-        }
-    }
-    *out = b;
+    BufOwner o;
+    EC_TRY(new_buf(ct, len, &o.b));
+    if (len && staged_wanted(host, len * kSize[ct])) EC_TRY(staged_upload(o.b, host));
+    else if (len) EC_CUDA_TRY(cudaMemcpyAsync(o.b->dptr, host, len * kSize[ct], cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
+    *out = o.release();
     return EC_OK;
 }
 ec_status ec_buf_from_host_async(uint8_t ct, const void* host, size_t len, ec_buf** out) {
@@ -1554,7 +1566,9 @@ ec_status ec_buf_from_host_async(uint8_t ct, const void* host, size_t len, ec_bu
     BufOwner o;
     EC_TRY(new_buf(ct, len, &o.b));
     ec_buf* b = o.b;
-    if (len) {
+    if (len && staged_wanted(host, len * kSize[ct])) {
+        EC_TRY(staged_upload(b, host));  // pageable memory: nothing to wait for afterwards
+    } else if (len) {
         const cudaStream_t up = g_ctx.dev[t_dev].upload;
         EC_CUDA_TRY(cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming), "cudaEventCreate");
         // the block may have been recycled from work still queued on the current stream: upload after it
@@ -1656,6 +1670,10 @@ ec_status ec_buf_to_host(const ec_buf* b, void* host, size_t host_bytes) {
     if (is_sharded(b)) return sh_to_host(b, host);
     DevScope on(b->dev);
     EC_TRY(resolve(b));
+    if (bytes && staged_wanted(host, bytes)) {
+        const HostSeg seg{b->dev, const_cast<void*>(rd(b)), host, bytes, cur_stream()};
+        return staged_transfer(&seg, 1, false);
+    }
     if (bytes) EC_CUDA_TRY(cudaMemcpyAsync(host, rd(b), bytes, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
     return sync_stream();
 }

@@ -142,6 +142,11 @@ using MaskMap2Fn = std::function<ec_status(const ec_mask*, const ec_mask* /* may
 int sh_part_of(const std::vector<size_t>& offs, size_t index);
 ec_status sh_generate(uint8_t ct, size_t len, const GenFn& fn, ec_buf** out);
 ec_status shm_generate(size_t len, const MaskGenFn& fn, ec_mask** out);
+// ---- pageable host memory (ec_ingest.inc): copies between a Vec<T> and HBM go through pinned staging chunks, moved
+// by a pool of host threads while the DMA of the previous chunk runs
+struct HostSeg { int dev; void* d; void* h; size_t bytes; cudaStream_t stream; };
+bool staged_wanted(const void* host, size_t bytes);                    // large, and neither pinned nor registered
+ec_status staged_transfer(const HostSeg* segs, int n, bool to_device);  // returns with every byte in place
 ec_status sh_from_host(uint8_t ct, const void* host, size_t len, bool async, ec_buf** out);
 ec_status sh_to_host(const ec_buf* b, void* host);
 ec_status sh_view(const ec_buf* b, size_t off, size_t len, ec_buf** out);

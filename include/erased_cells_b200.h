@@ -206,6 +206,13 @@ ec_status ec_ingest_next_buffer(ec_ingest* g, void** host_chunk, size_t* capacit
 ec_status ec_ingest_submit(ec_ingest* g, size_t n_cells);
 ec_status ec_ingest_finish(ec_ingest* g, ec_buf** out_buf, ec_mask** out_mask_or_null);
 void ec_ingest_abort(ec_ingest* g);
+/* CellBuffer::from_vec / to_vec on a Vec<T> (pageable memory, src/buffer.rs:60-66, :175-188): copies of >= 16 MiB between
+ * memory that is neither pinned nor registered and HBM are moved 8 MiB at a time through pinned staging by `threads` host
+ * threads (the caller among them) while the DMA engine moves the previous chunks; with several GPUs the chunks alternate
+ * between the strips' links. 0 = leave pageable copies to the CUDA driver (one staging buffer, one thread). Default:
+ * $EC_HOST_COPY_THREADS, else min(12, cores - 2). Pinned or registered memory is always copied directly. Returns the
+ * previous setting. */
+int ec_set_host_copy_threads(int threads);
 /* with_defaults (:68-77) */
 ec_status ec_buf_with_defaults(size_t len, uint8_t ct, ec_buf** out);
 /* fill (:79-88): type = the value's type */

@@ -101,3 +101,31 @@ def test_chunked_ingest_matches_one_shot_upload(orc, tmp_path):
     m = raster_io.read_cells_masked(p, chunk_cells=1024)
     assert np.array_equal(m.buffer().to_vec(), whole.reshape(-1)) and m.counts() == (int((px != 0).sum()), int((px == 0).sum()))
     assert raster_io.read_cells(p, wait=True) == CellBuffer.from_vec(px.reshape(-1))
+
+
+@pytest.mark.gpu
+def test_pageable_from_vec_and_to_vec_go_through_the_staging_threads():
+    """from_vec / to_vec on a Vec<T> (src/buffer.rs:60-66, :175-188; numpy arrays are pageable memory like a Vec): copies
+    of >= 16 MiB run through the staged path (8 MiB chunks, a pool of host threads); ragged sizes, every thread count,
+    the driver's own path (0) and pinned memory must all give the same bits."""
+    import torch
+    from erased_cells_b200 import synth
+    try:
+        for ct, n in ((CellType.UInt8, (16 << 20) + 1), (CellType.Float64, (3 << 20) + 77), (CellType.Int16, (20 << 20) - 3)):
+            h = synth.host(ct, n, 0xC0B1 + int(ct))
+            pinned = torch.empty(h.nbytes, dtype=torch.uint8).pin_memory().numpy().view(h.dtype)
+            pinned[:] = h
+            want = CellBuffer.from_vec(pinned)  # pinned memory: always the direct copy
+            for threads in (0, 1, 2, 5, 12):
+                ec.set_host_copy_threads(threads)
+                b = CellBuffer.from_vec(h)
+                assert b == want, (ct, threads)
+                out = b.to_vec()
+                assert out.dtype == h.dtype and np.array_equal(out.view(np.uint8), h.view(np.uint8)), (ct, threads)
+                a = CellBuffer.from_vec(h, wait=False).wait()
+                assert a == want, (ct, threads, "async")
+                sink = np.zeros(n + 5, dtype=h.dtype)
+                assert np.array_equal(b.to_vec(out=sink).view(np.uint8), h.view(np.uint8)) and not sink[n:].any()
+        assert ec.set_host_copy_threads(7) == 12
+    finally:
+        ec.set_host_copy_threads(int(__import__("os").environ.get("EC_HOST_COPY_THREADS", 12)))

@@ -52,6 +52,18 @@ small = CellBuffer.from_vec(a_h[:1000])
 assert small.shard_count() == 0  # below the threshold: one GPU
 assert a.device_ptr() == 0       # a sharded buffer has no single device pointer
 
+# ---- pageable host memory of >= 16 MiB: the staged copy, chunks alternating between the strips ----------------------------
+big_n = (17 << 20) + 12345  # u16: 34 MiB, ragged against the 8 MiB chunks and the 128-cell strips
+big_h = synth.host(CellType.UInt16, big_n, 0x51A6)
+for threads in (0, 1, 3):
+    prev = ec.set_host_copy_threads(threads)
+    big = CellBuffer.from_vec(big_h)
+    assert big.shard_count() == G
+    same(big.to_vec(), big_h, f"pageable round trip, {threads} copy threads")
+    same(CellBuffer.from_vec(big_h, wait=False).wait().to_vec(), big_h, f"pageable async round trip, {threads} copy threads")
+    del big
+    ec.set_host_copy_threads(prev)
+
 # ---- maps: all four ops on mixed types, scalar, neg, convert, clone -------------------------------------------------
 for op in range(4):
     same((a._bin(op, b)).to_vec(), orc.tight_binary(op, a_h, b_h), f"binary {op}")
