@@ -3,9 +3,6 @@
 // reference file:line each entry point replaces.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
-#if defined(__x86_64__)
-#include <immintrin.h>
-#endif
 
 #include <atomic>
 #include <cmath>
@@ -21,6 +18,7 @@
 #include <thread>
 #include <vector>
 
+#include "ec_hostcopy.hpp"
 #include "ec_internal.hpp"
 #include "ec_reduce.cuh"
 

@@ -32,3 +32,11 @@ def test_cpp_port_builds_on_cpu():
     subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "-s"], check=True)
     assert os.path.exists(os.path.join(ROOT, "tests", "cpp", "build", "test_reference_port"))
     assert os.path.exists(os.path.join(ROOT, "tests", "cpp", "build", "abi_smoke_c"))  # the header is valid C99 (-pedantic -Werror)
+
+
+def test_host_copy_pool_on_cpu():
+    """CPU: the thread pool that moves pageable memory to / from pinned staging (csrc/ec_hostcopy.hpp) — ragged sizes,
+    every thread count, concurrent callers, and a process exit while the workers sleep."""
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "-s", "build/test_hostcopy"], check=True)
+    r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "build", "test_hostcopy")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "HOSTCOPY_OK" in r.stdout, r.stdout + r.stderr

@@ -110,6 +110,7 @@ def test_pageable_from_vec_and_to_vec_go_through_the_staging_threads():
     the driver's own path (0) and pinned memory must all give the same bits."""
     import torch
     from erased_cells_b200 import synth
+    default = ec.set_host_copy_threads(1)
     try:
         for ct, n in ((CellType.UInt8, (16 << 20) + 1), (CellType.Float64, (3 << 20) + 77), (CellType.Int16, (20 << 20) - 3)):
             h = synth.host(ct, n, 0xC0B1 + int(ct))
@@ -128,4 +129,4 @@ def test_pageable_from_vec_and_to_vec_go_through_the_staging_threads():
                 assert np.array_equal(b.to_vec(out=sink).view(np.uint8), h.view(np.uint8)) and not sink[n:].any()
         assert ec.set_host_copy_threads(7) == 12
     finally:
-        ec.set_host_copy_threads(int(__import__("os").environ.get("EC_HOST_COPY_THREADS", 12)))
+        ec.set_host_copy_threads(default)
