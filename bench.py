@@ -441,6 +441,28 @@ def run_ours(args, out):
                             "note": "peak = this rank's bare D2H rate while all ranks copy at once (the host side is shared); "
                                     "the step moves d2h_bytes_per_step per rank"},
                "api": "CellBuffer.from_vec(pinned host, wait=False: next source prefetched) -> convert(ct) -> to_vec(pinned host), per rank"}
+        if world == 1:
+            # The crate's own callers hold Vec<T>: PAGEABLE memory. Same step from / into numpy arrays, once through the
+            # library's staged path (8 MiB chunks via pinned staging, a pool of host threads) and once leaving the pageable
+            # copies to the CUDA driver (ec_set_host_copy_threads(0)).
+            pinned_src, pinned_out = hsrc, rawout
+            hsrc = [np.array(a) for a in pinned_src]
+            rawout = np.zeros(cells * 8, dtype=np.uint8)
+            threads = L.ec_set_host_copy_threads(0)
+            pageable = {}
+            for label, t in (("driver", 0), ("staged", threads)):
+                L.ec_set_host_copy_threads(t)
+                e2e_step()
+                t0 = time.perf_counter()
+                chk = e2e_step()
+                ms = (time.perf_counter() - t0) * 1e3
+                pageable[label] = {"value": round(len(pairs) * cells / (ms * 1e-3) / 1e9, 3), "ms_per_step": round(ms, 1), "host_copy_threads": t,
+                                   "d2h_GBps": round(d2h / (ms * 1e-3) / 1e9, 2), "checksum": chk}
+            assert pageable["driver"]["checksum"] == pageable["staged"]["checksum"]
+            pageable["what"] = ("same step with numpy (pageable) sources and destination, what a Vec<T> caller sees: 'staged' = the library's "
+                                "chunked copy through pinned staging with a pool of host threads, 'driver' = cudaMemcpy on pageable memory")
+            e2e["pageable"] = pageable
+            hsrc, rawout = pinned_src, pinned_out
         for p in keep + [pout]:
             L.ec_host_free(p)
     del srcs

@@ -3,6 +3,7 @@
 // reference file:line each entry point replaces.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sys/mman.h>
 
 #include <atomic>
 #include <cmath>
@@ -2087,7 +2088,12 @@ ec_status ec_mask_from_bools(const uint8_t* host_bools, size_t len, ec_mask** ou
     if (len) {
         Scratch stage;
         EC_TRY(stage.alloc(len));
-        EC_CUDA_TRY(cudaMemcpyAsync(stage.p, host_bools, len, cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
+        if (staged_wanted(host_bools, len)) {  // a Vec<bool>: the staged copy, on the stream the pack kernel follows on
+            const HostSeg seg{t_dev, stage.p, const_cast<uint8_t*>(host_bools), len, cur_stream()};
+            EC_TRY(staged_transfer(&seg, 1, true));
+        } else {
+            EC_CUDA_TRY(cudaMemcpyAsync(stage.p, host_bools, len, cudaMemcpyHostToDevice, cur_stream()), "cudaMemcpyAsync(H2D)");
+        }
         EC_LAUNCH(launch_mask_build(launch_ctx(), 1, stage.p, len, 0, true, m->words, arm_count(m)), "mask_pack");
     }
     *out = hold.release();
@@ -2117,6 +2123,10 @@ ec_status ec_mask_to_bools(const ec_mask* m, uint8_t* host_bools, size_t capacit
     Scratch stage;
     EC_TRY(stage.alloc(m->len));
     EC_LAUNCH(launch_mask_unpack(launch_ctx(), rdm(m), m->len, static_cast<uint8_t*>(stage.p)), "mask_unpack");
+    if (staged_wanted(host_bools, m->len)) {
+        const HostSeg seg{m->dev, stage.p, host_bools, m->len, cur_stream()};
+        return staged_transfer(&seg, 1, false);
+    }
     EC_CUDA_TRY(cudaMemcpyAsync(host_bools, stage.p, m->len, cudaMemcpyDeviceToHost, cur_stream()), "cudaMemcpyAsync(D2H)");
     return sync_stream();
 }

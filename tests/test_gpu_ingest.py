@@ -127,6 +127,11 @@ def test_pageable_from_vec_and_to_vec_go_through_the_staging_threads():
                 assert a == want, (ct, threads, "async")
                 sink = np.zeros(n + 5, dtype=h.dtype)
                 assert np.array_equal(b.to_vec(out=sink).view(np.uint8), h.view(np.uint8)) and not sink[n:].any()
+        bools = synth.host(CellType.UInt8, (17 << 20) + 9, 0xB001) > 100  # a Vec<bool> of 17 Mi cells (src/masked/mask.rs:120-131)
+        for threads in (0, 3, 12):
+            ec.set_host_copy_threads(threads)
+            m = Mask.new(bools)
+            assert m.counts() == (int(bools.sum()), int((~bools).sum())) and np.array_equal(m.to_vec(), bools), threads
         assert ec.set_host_copy_threads(7) == 12
     finally:
         ec.set_host_copy_threads(default)
