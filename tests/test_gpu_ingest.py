@@ -127,6 +127,19 @@ def test_pageable_from_vec_and_to_vec_go_through_the_staging_threads():
                 assert a == want, (ct, threads, "async")
                 sink = np.zeros(n + 5, dtype=h.dtype)
                 assert np.array_equal(b.to_vec(out=sink).view(np.uint8), h.view(np.uint8)) and not sink[n:].any()
+        # several caller threads at once (ctypes drops the GIL): the transfers take turns on the copy pool chunk by chunk
+        from concurrent.futures import ThreadPoolExecutor
+        ec.set_host_copy_threads(4)
+        arrays = [synth.host(CellType.UInt16, (9 << 20) + 1000 * k, 0xAB00 + k) for k in range(4)]
+
+        def round_trip(a):
+            for _ in range(3):
+                if not np.array_equal(CellBuffer.from_vec(a).to_vec(), a):
+                    return False
+            return True
+
+        with ThreadPoolExecutor(4) as pool:
+            assert all(pool.map(round_trip, arrays))
         bools = synth.host(CellType.UInt8, (17 << 20) + 9, 0xB001) > 100  # a Vec<bool> of 17 Mi cells (src/masked/mask.rs:120-131)
         for threads in (0, 3, 12):
             ec.set_host_copy_threads(threads)
