@@ -65,6 +65,8 @@ inline int init_devices(const std::vector<int>& devices) {
     return ec_device_count();
 }
 inline size_t set_shard_min_cells(size_t cells) { return ec_set_shard_min_cells(cells); }
+// host threads that move pageable memory (std::vector) to / from pinned staging under the DMA; 0 = the driver's own path
+inline int set_host_copy_threads(int threads) { return ec_set_host_copy_threads(threads); }
 
 // ---- CellEncoding — src/encoding.rs:9-40 ----------------------------------------------------------
 template <class T> struct CellEncoding;  // only the ten primitives are CellEncoding
@@ -179,6 +181,7 @@ class CellBuffer {
     static CellBuffer own(ec_buf* h) { CellBuffer b; b.h_ = h; return b; }
     friend class MaskedCellBuffer;
     friend class Mask;
+    template <class T> friend class Ingest;
 
 public:
     CellBuffer() = default;
@@ -271,8 +274,11 @@ inline bool operator>(const CellBuffer& l, const CellBuffer& r) { return l.cmp(r
 // ---- Mask — src/masked/mask.rs -------------------------------------------------------------------------------------
 class Mask {
     ec_mask* h_ = nullptr;
-    static Mask own(ec_mask* h) { Mask m; m.h_ = h; return m; }
+    struct Adopt {};
+    Mask(ec_mask* h, Adopt) : h_(h) {}
+    static Mask own(ec_mask* h) { return Mask(h, Adopt{}); }
     friend class MaskedCellBuffer;
+    template <class T> friend class Ingest;
 
 public:
     Mask() { detail::check(ec_mask_fill(0, 1, &h_)); }  // Default
@@ -423,6 +429,59 @@ public:
     bool operator==(const MaskedCellBuffer& o) const { return buf_ == o.buf_ && mask_ == o.mask_; }
     bool operator!=(const MaskedCellBuffer& o) const { return !(*this == o); }
 };
+// ---- chunked ingest (extension): what the GDAL adapter's read_cells / read_cells_masked (src/gdal/rasterband.rs:81-126)
+// become when the reader produces the band block by block. The reader fills pinned staging buffers handed out one at
+// a time; uploads, NoData compares and the reader overlap.
+//     Ingest<uint16_t> in(len, NoData<uint16_t>::new_(0));
+//     while (auto chunk = in.next()) { size_t n = read_rows(chunk.data, chunk.capacity); in.submit(n); }
+//     MaskedCellBuffer band = in.finish_masked();
+template <class T> class Ingest {
+    ec_ingest* g_ = nullptr;
+    bool masked_ = false;
+
+public:
+    struct Chunk {
+        T* data = nullptr;
+        size_t capacity = 0;  // cells
+        explicit operator bool() const { return data != nullptr; }
+    };
+    explicit Ingest(size_t len, size_t chunk_cells = 0) {  // read_cells: no mask
+        detail::check(ec_ingest_begin(uint8_t(CellEncoding<T>::cell_type()), len, EC_NODATA_NONE, nullptr, 0, chunk_cells, &g_));
+    }
+    Ingest(size_t len, NoData<T> nodata, size_t chunk_cells = 0) : masked_(true) {  // read_cells_masked
+        const CellValue cv(nodata.v);
+        detail::check(ec_ingest_begin(uint8_t(CellEncoding<T>::cell_type()), len, nodata.kind, &cv.v, 1, chunk_cells, &g_));
+    }
+    Ingest(const Ingest&) = delete;
+    Ingest& operator=(const Ingest&) = delete;
+    ~Ingest() { if (g_) ec_ingest_abort(g_); }
+    Chunk next() {  // empty once every cell has been submitted
+        void* p;
+        size_t cap;
+        detail::check(ec_ingest_next_buffer(g_, &p, &cap));
+        Chunk c;
+        c.data = static_cast<T*>(p);
+        c.capacity = cap;
+        return c;
+    }
+    void submit(size_t n_cells) { detail::check(ec_ingest_submit(g_, n_cells)); }
+    CellBuffer finish() {
+        ec_buf* b;
+        ec_ingest* g = g_;
+        detail::check(ec_ingest_finish(g, &b, nullptr));
+        g_ = nullptr;
+        return CellBuffer::own(b);
+    }
+    MaskedCellBuffer finish_masked() {
+        if (!masked_) throw std::logic_error("Ingest: begun without a NoData (read_cells); use finish()");
+        ec_buf* b;
+        ec_mask* m;
+        detail::check(ec_ingest_finish(g_, &b, &m));
+        g_ = nullptr;
+        return MaskedCellBuffer(CellBuffer::own(b), Mask::own(m));
+    }
+};
+
 #define EC_HPP_MBUF_OP(sym, code)                                                                                                       \
     inline MaskedCellBuffer operator sym(const MaskedCellBuffer& l, const MaskedCellBuffer& r) { return MaskedCellBuffer::binary(code, l, r); } \
     inline MaskedCellBuffer operator sym(const MaskedCellBuffer& l, const CellValue& r) { return MaskedCellBuffer::scalar(code, l, r); }       \

@@ -83,6 +83,13 @@ pub fn init_devices(devices: &[i32]) -> Result<()> {
     check(unsafe { ec_init_devices(devices.as_ptr(), devices.len() as i32) })
 }
 
+/// Extension: host threads that move a `Vec<T>` (pageable memory) to / from pinned staging while the DMA engine copies the
+/// previous chunks (`from_vec`, `to_vec`, `Mask::new` of at least 16 MiB). 0 leaves such copies to the CUDA driver.
+/// Returns the previous setting.
+pub fn set_host_copy_threads(threads: i32) -> i32 {
+    unsafe { ec_set_host_copy_threads(threads) }
+}
+
 // ---- DeviceVec<T>: what a CellBuffer variant holds instead of Vec<T> ------------------------------------------
 /// `len` cells of `T` in HBM, owned. `#[repr(transparent)]` over the C handle: no cost over the raw pointer.
 /// Send + Sync: kernels only read their inputs, handles are uniquely owned.
@@ -826,6 +833,75 @@ impl<'de> Deserialize<'de> for MaskedCellBuffer {
         wire::MaskedWire::deserialize(d).map(|w| MaskedCellBuffer::new(w.0.into(), Mask::new((w.1).0)))
     }
 }
+/// Extension: chunked ingest — what `read_cells` / `read_cells_masked` (src/gdal/rasterband.rs:81-126) become when the
+/// band is read block by block instead of into one `Vec`. The reader fills pinned staging slices handed out one at a
+/// time; the upload of chunk k, the read of chunk k + 1 and the NoData compare of chunk k − 1 overlap, and on a
+/// multi-GPU library every chunk goes straight to the GPU that owns its row strip.
+/// ```ignore
+/// let mut ingest = Ingest::<u16>::masked(len, NoData::new(0));
+/// while let Some(chunk) = ingest.next_chunk() {
+///     let n = band.read_block_into(chunk)?;   // fills chunk[..n]
+///     ingest.submit(n);
+/// }
+/// let band: MaskedCellBuffer = ingest.finish_masked();
+/// ```
+pub struct Ingest<T: CellEncoding> {
+    g: *mut ec_ingest,
+    masked: bool,
+    _cells: PhantomData<T>,
+}
+impl<T: CellEncoding> Ingest<T> {
+    /// `read_cells`: cells only.
+    pub fn new(len: usize) -> Self {
+        let mut g = ptr::null_mut();
+        check(unsafe { ec_ingest_begin(T::cell_type() as u8, len, 0, ptr::null(), 0, 0, &mut g) }).unwrap();
+        Self { g, masked: false, _cells: PhantomData }
+    }
+    /// `read_cells_masked`: the validity mask is built from `nodata` chunk by chunk (`NoData::None`: all valid).
+    pub fn masked(len: usize, nodata: NoData<T>) -> Self {
+        let (kind, v) = nodata_ffi(nodata);
+        let mut g = ptr::null_mut();
+        check(unsafe { ec_ingest_begin(T::cell_type() as u8, len, kind, &v, 1, 0, &mut g) }).unwrap();
+        Self { g, masked: true, _cells: PhantomData }
+    }
+    /// The next staging slice to fill, `None` once every cell has been submitted. Blocks while the upload that last
+    /// used this slice is still reading it.
+    pub fn next_chunk(&mut self) -> Option<&mut [T]> {
+        let (mut p, mut cap) = (ptr::null_mut(), 0usize);
+        check(unsafe { ec_ingest_next_buffer(self.g, &mut p, &mut cap) }).unwrap();
+        if p.is_null() {
+            None
+        } else {
+            Some(unsafe { std::slice::from_raw_parts_mut(p.cast::<T>(), cap) })
+        }
+    }
+    /// The first `n_cells` of the slice handed out last are valid (a short chunk must be a multiple of 128 cells unless
+    /// it is the last one).
+    pub fn submit(&mut self, n_cells: usize) {
+        check(unsafe { ec_ingest_submit(self.g, n_cells) }).unwrap();
+    }
+    pub fn finish(mut self) -> CellBuffer {
+        let mut b = ptr::null_mut();
+        check(unsafe { ec_ingest_finish(self.g, &mut b, ptr::null_mut()) }).unwrap();
+        self.g = ptr::null_mut();
+        CellBuffer::wrap(b)
+    }
+    pub fn finish_masked(mut self) -> MaskedCellBuffer {
+        assert!(self.masked, "Ingest::new reads cells only; use Ingest::masked");
+        let (mut b, mut m) = (ptr::null_mut(), ptr::null_mut());
+        check(unsafe { ec_ingest_finish(self.g, &mut b, &mut m) }).unwrap();
+        self.g = ptr::null_mut();
+        MaskedCellBuffer(CellBuffer::wrap(b), Mask::own(m))
+    }
+}
+impl<T: CellEncoding> Drop for Ingest<T> {
+    fn drop(&mut self) {
+        if !self.g.is_null() {
+            unsafe { ec_ingest_abort(self.g) } // abandoned half way: frees what was uploaded so far
+        }
+    }
+}
+
 /// Result of the `statistics()` extension.
 #[derive(Debug, Clone, Copy, PartialEq)]
 pub struct Statistics {

@@ -269,8 +269,50 @@ static void statistics_tests() {
     CHECK(big.mean == 4000000001.0 && big.stddev == 1.0);
 }
 
+// Chunked ingest (the GDAL adapter's read_cells / read_cells_masked, src/gdal/rasterband.rs:81-126, fed block by block) and the
+// staged copy of a pageable std::vector: both must give what the one-shot constructors give.
+static void ingest_tests() {
+    const size_t n = 300 * 1000 + 37;
+    std::vector<uint16_t> band(n);
+    uint32_t x = 7;
+    for (auto& v : band) { x = x * 1664525u + 1013904223u; v = (x >> 28) == 0 ? 0 : uint16_t(x >> 12); }
+    Ingest<uint16_t> in(n, NoData<uint16_t>::new_(0), 4096);
+    size_t pos = 0;
+    while (auto chunk = in.next()) {
+        const size_t k = std::min(chunk.capacity, n - pos);
+        std::copy(band.begin() + pos, band.begin() + pos + k, chunk.data);
+        in.submit(k);
+        pos += k;
+    }
+    CHECK(pos == n);
+    const MaskedCellBuffer chunked = in.finish_masked();
+    const MaskedCellBuffer one_shot = MaskedCellBuffer::from_vec_with_nodata(band, NoData<uint16_t>::new_(0));
+    CHECK(chunked == one_shot && chunked.counts() == one_shot.counts() && chunked.counts().second > 0);
+    Ingest<uint16_t> plain(n);
+    pos = 0;
+    while (auto chunk = plain.next()) {
+        const size_t k = std::min(chunk.capacity, n - pos);
+        std::copy(band.begin() + pos, band.begin() + pos + k, chunk.data);
+        plain.submit(k);
+        pos += k;
+    }
+    CHECK(plain.finish() == CellBuffer::from_vec(band));
+    { Ingest<uint16_t> dropped(n); (void)dropped.next(); }  // abandoned half way: the destructor aborts it
+
+    std::vector<double> big((size_t(3) << 20) + 5);  // 24 MiB of pageable memory: the staged copy
+    for (size_t i = 0; i < big.size(); ++i) big[i] = double(i) * 0.25 - 1000.0;
+    for (int threads : {0, 1, 6}) {
+        const int prev = set_host_copy_threads(threads);
+        const CellBuffer b = CellBuffer::from_vec(big);
+        const std::vector<double> back = b.to_vec<double>();
+        CHECK(back == big);
+        set_host_copy_threads(prev);
+    }
+}
+
 int main() {
     try {
+        ingest_tests();
         can_union(); ctype_misc(); value_tests(); buffer_tests(); mask_tests(); nodata_tests(); masked_tests(); lazy_tests();
         statistics_tests();
     } catch (const std::exception& e) {
