@@ -661,6 +661,31 @@ def strong_scaling(ec, L, torch, dist, rank, world, local, barrier, max_over_ran
     res["c4_f32_32768_min_max"] = entry(ms, wall, 4.0 * n4, n4, n1_ms, shards=world, result_bits=list(got_fused), expected_bits=list(want),
                                         finish=("ec_buf_min_max_sharded: reduction + NVLink peer exchange + fold in ONE kernel per GPU, result polled from mapped pinned memory"
                                                 if comm is not None and comm.peer_exchange else "ec_buf_min_max (one GPU)" if comm is None else "kernel + ncclAllReduce (ec_comm)"))
+    # the same 40 calls issued by a C loop (tools/call_loop.c): a compiled caller, no interpreter between the calls
+    loop_so = os.path.join(ROOT, "tools", "bin", "libec_call_loop.so")
+    if os.path.exists(loop_so):
+        LL = C.CDLL(loop_so)
+        LL.ec_loop_min_max.restype = C.c_int
+        LL.ec_loop_min_max.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        comm_h = comm._h if comm is not None else None
+
+        def c_loop(iters):
+            ec._lib.check(LL.ec_loop_min_max(comm_h, strip._h, iters, C.byref(vmn), C.byref(vmx)))
+
+        c_loop(10)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        c_loop(40)
+        b.record()
+        torch.cuda.current_stream().synchronize()
+        wall_c = max_over_ranks((time.perf_counter() - t0) * 1e3 / 40)
+        barrier()
+        ms_c = max_over_ranks(a.elapsed_time(b)) / 40
+        parity["c4_min_max_after_c_loop"] = (hex(vmn.bits), hex(vmx.bits)) == want
+        res["c4_f32_32768_min_max_c_loop"] = entry(ms_c, wall_c, 4.0 * n4, n4, n1_ms, shards=world, result_bits=[hex(vmn.bits), hex(vmx.bits)],
+                                                   finish="same entry point as c4_f32_32768_min_max, the 40 timed calls issued back to back from C (tools/call_loop.c)")
     ms, wall = timed(c4_nccl, 20)
     res["c4_f32_32768_min_max_nccl"] = entry(ms, wall, 4.0 * n4, n4, n1_ms, shards=world, result_bits=list(got_nccl),
                                              finish="shard kernel + torch.distributed all-reduce(MIN, 2 x int64) + D2H of the result")
