@@ -210,7 +210,8 @@ void ec_ingest_abort(ec_ingest* g);
  * memory that is neither pinned nor registered and HBM are moved 8 MiB at a time through pinned staging by `threads` host
  * threads (the caller among them) while the DMA engine moves the previous chunks; with several GPUs the chunks alternate
  * between the strips' links. 0 = leave pageable copies to the CUDA driver (one staging buffer, one thread). Default:
- * $EC_HOST_COPY_THREADS, else min(8, cores - 2), min(12, cores - 2) when the copy spans several GPUs' links. Pinned or registered memory is always copied directly. Returns the
+ * $EC_HOST_COPY_THREADS, else (also for threads < 0) min(8, cores - 2), min(12, cores - 2) when the copy spans several GPUs'
+ * links or lands in memory whose pages do not exist yet (a fresh Vec: page-fault bound). Pinned or registered memory is always copied directly. Returns the
  * previous setting. */
 int ec_set_host_copy_threads(int threads);
 /* with_defaults (:68-77) */

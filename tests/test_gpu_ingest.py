@@ -110,7 +110,7 @@ def test_pageable_from_vec_and_to_vec_go_through_the_staging_threads():
     the driver's own path (0) and pinned memory must all give the same bits."""
     import torch
     from erased_cells_b200 import synth
-    default = ec.set_host_copy_threads(1)
+    ec.set_host_copy_threads(1)
     try:
         for ct, n in ((CellType.UInt8, (16 << 20) + 1), (CellType.Float64, (3 << 20) + 77), (CellType.Int16, (20 << 20) - 3)):
             h = synth.host(ct, n, 0xC0B1 + int(ct))
@@ -147,4 +147,4 @@ def test_pageable_from_vec_and_to_vec_go_through_the_staging_threads():
             assert m.counts() == (int(bools.sum()), int((~bools).sum())) and np.array_equal(m.to_vec(), bools), threads
         assert ec.set_host_copy_threads(7) == 12
     finally:
-        ec.set_host_copy_threads(default)
+        ec.set_host_copy_threads(-1)  # back to the default

@@ -68,7 +68,7 @@ def to_fresh_mmap():  # anonymous pages straight from the kernel, no huge-page a
     return out
 
 
-for threads in [int(a) for a in sys.argv[1:]] or [0, 1, 4, 8, 12, 16]:
+for threads in [int(a) for a in sys.argv[1:]] or [0, -1, 1, 4, 8, 12, 16]:
     ec.set_host_copy_threads(threads)
     up = best(lambda: CellBuffer.from_vec(band))
     down_fresh = best(lambda: resident.to_vec())
@@ -76,7 +76,7 @@ for threads in [int(a) for a in sys.argv[1:]] or [0, 1, 4, 8, 12, 16]:
     down_mmap = best(to_fresh_mmap)
     b = CellBuffer.from_vec(band)
     assert b == resident and np.array_equal(resident.to_vec(), band) and np.array_equal(touched, band), "staged copy differs"
-    label = "driver (pageable cudaMemcpy)" if threads == 0 else f"staged, {threads} thread{'s' if threads > 1 else ''}"
+    label = "driver (pageable cudaMemcpy)" if threads == 0 else "staged, default threads" if threads < 0 else f"staged, {threads} thread{'s' if threads > 1 else ''}"
     print(f"{label}: from_vec {nbytes / up / 1e9:.1f} GB/s ({h2d / up:.2f} of the link) | to_vec into fresh memory "
           f"{nbytes / down_fresh / 1e9:.1f} GB/s ({d2h / down_fresh:.2f}) | to_vec into touched memory {nbytes / down / 1e9:.1f} GB/s ({d2h / down:.2f}) "
           f"| to_vec into a fresh plain mmap {nbytes / down_mmap / 1e9:.1f} GB/s ({d2h / down_mmap:.2f})")
