@@ -143,9 +143,43 @@ static Launch launch_ctx() {
 // (profiles/r02_pdl_reductions.txt). $EC_PDL_REDUCE_ATTR=1 brings the attribute back for the A/B.
 static Launch launch_ctx_reduce() {
     static const int attr = env_int("EC_PDL_REDUCE_ATTR", 0);
+    static const int graph = env_int("EC_GRAPH_REDUCE", 1);  // 0: ordinary stream launches (A/B)
     Launch l = launch_ctx();
     l.overlap = l.overlap && attr;
+    l.graph = graph != 0;
     return l;
+}
+// Slots of the graph-launched reductions: per (kernel, CUDA device) a short list; a launch takes the first slot nobody is
+// updating (two threads reducing at once each get their own graph). Never destroyed: they live as long as the context.
+struct GraphSlots {
+    std::mutex mu;
+    std::map<std::pair<const void*, int>, std::vector<std::unique_ptr<GraphSlot>>> slots;
+};
+static GraphSlots& graph_slots() {
+    static GraphSlots* g = new GraphSlots;
+    return *g;
+}
+GraphSlot* graph_slot_acquire(const void* func) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    struct Cached { const void* func; int dev; GraphSlot* slot; };
+    static thread_local Cached last[4] = {};  // the reductions a thread keeps calling: no lock, no map lookup
+    for (Cached& c : last)
+        if (c.func == func && c.dev == dev && c.slot && !c.slot->busy.test_and_set(std::memory_order_acquire)) return c.slot;
+    GraphSlots& g = graph_slots();
+    std::lock_guard<std::mutex> lk(g.mu);
+    auto& list = g.slots[{func, dev}];
+    GraphSlot* got = nullptr;
+    for (auto& s : list)
+        if (!s->busy.test_and_set(std::memory_order_acquire)) { got = s.get(); break; }
+    if (!got) {
+        list.emplace_back(new GraphSlot);
+        got = list.back().get();
+        got->busy.test_and_set(std::memory_order_acquire);
+    }
+    static thread_local unsigned turn = 0;
+    last[turn++ % 4] = Cached{func, dev, got};
+    return got;
 }
 int n_devices() { return g_ctx.n_dev; }
 int device_phys(int dev) { return g_ctx.dev[dev].phys; }
