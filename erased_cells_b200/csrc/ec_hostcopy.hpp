@@ -44,15 +44,19 @@ __attribute__((target("avx2"))) static void copy_stream_avx2(char* d, const char
     if (n) memcpy(d, s, n);
 }
 #endif
-static int g_copy_nt = -1;
+static std::atomic<int> g_copy_nt{-1};  // -1: not decided yet; 0 memcpy; 1 streaming stores (several threads may decide at once: same answer)
 static bool copy_stream_env() {
     const char* v = getenv("EC_HOST_COPY_STREAM");
     return !v || atoi(v) != 0;
 }
 static void copy_piece(char* d, const char* s, size_t n) {
 #if defined(__x86_64__)
-    if (g_copy_nt < 0) g_copy_nt = copy_stream_env() && __builtin_cpu_supports("avx2");
-    if (g_copy_nt) { copy_stream_avx2(d, s, n); return; }
+    int nt = g_copy_nt.load(std::memory_order_relaxed);
+    if (nt < 0) {
+        nt = copy_stream_env() && __builtin_cpu_supports("avx2");
+        g_copy_nt.store(nt, std::memory_order_relaxed);
+    }
+    if (nt) { copy_stream_avx2(d, s, n); return; }
 #endif
     memcpy(d, s, n);
 }
