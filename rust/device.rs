@@ -17,6 +17,7 @@ use crate::error::{Error, Result};
 use crate::ffi::*;
 use crate::{with_ct, BufferOps, CellEncoding, CellType, CellValue, NoData};
 use std::cmp::Ordering;
+use std::fmt::{Debug, Formatter};
 use std::marker::PhantomData;
 use std::ops::{Add, BitAnd, BitOr, Div, Index, IndexMut, Mul, Neg, Not, Sub};
 use std::ptr;
@@ -123,6 +124,23 @@ impl<T: CellEncoding> DeviceVec<T> {
     /// Row strips this buffer is kept as (0: one GPU).
     pub fn shard_count(&self) -> usize {
         unsafe { ec_buf_shard_count(self.h) as usize }
+    }
+    /// The cells `Debug` shows — all of up to ten, else the first and the last five (`Elided`, src/lib.rs:166-194):
+    /// one small D2H copy or ten single-cell reads, never the raster.
+    fn ends(&self) -> (Vec<T>, Vec<T>) {
+        let n = self.len();
+        if n <= 10 {
+            return (self.to_vec(), Vec::new());
+        }
+        let cell = |i: usize| -> T {
+            let mut v = ZERO_VALUE;
+            check(unsafe { ec_buf_get(self.h, i, &mut v) }).unwrap();
+            let mut out = T::zero();
+            // the payload is the cell's little-endian bytes in the low bytes of `bits`
+            unsafe { ptr::copy_nonoverlapping(v.bits.to_le_bytes().as_ptr(), (&mut out as *mut T).cast::<u8>(), std::mem::size_of::<T>()) };
+            out
+        };
+        ((0..5).map(cell).collect(), (n - 5..n).map(cell).collect())
     }
 }
 impl<T: CellEncoding> From<Vec<T>> for DeviceVec<T> {
@@ -387,6 +405,32 @@ impl PartialEq for CellBuffer {
     }
 }
 impl Eq for CellBuffer {}
+impl Debug for CellBuffer {
+    fn fmt(&self, f: &mut Formatter<'_>) -> std::fmt::Result {
+        // src/buffer.rs:188-203: `{type}CellBuffer(a, b, …)` with more than ten cells elided to five at either end
+        use crate::Elided;
+        let basename = self.cell_type().to_string();
+        macro_rules! render {
+            ( $(($id:ident, $_p:ident)),*) => {{
+                f.write_fmt(format_args!("{basename}CellBuffer("))?;
+                match self {
+                    $(CellBuffer::$id(b) => {
+                        let (head, tail) = b.ends();
+                        if !head.is_empty() {
+                            f.write_fmt(format_args!("{:?}", Elided(&head)))?;
+                        }
+                        if !tail.is_empty() {
+                            f.write_str(", ... ")?;
+                            f.write_fmt(format_args!("{:?}", Elided(&tail)))?;
+                        }
+                    })*
+                };
+                f.write_str(")")
+            }}
+        }
+        with_ct!(render)
+    }
+}
 
 // serde: the derive on `enum CellBuffer { UInt8(Vec<u8>), … }` (src/buffer.rs:51) is an externally tagged enum of
 // sequences. The same derive on a host-side twin with the same name and variants emits exactly that format.
@@ -553,6 +597,29 @@ impl Clone for Mask {
         let mut h = ptr::null_mut();
         check(unsafe { ec_mask_clone(self.h(), &mut h) }).unwrap();
         Self::own(h)
+    }
+}
+impl Default for Mask {
+    fn default() -> Self {
+        Mask::fill(0, true) // #[derive(Default)] on Mask(Vec<bool>) (src/masked/mask.rs:10): the empty mask
+    }
+}
+impl Debug for Mask {
+    fn fmt(&self, f: &mut Formatter<'_>) -> std::fmt::Result {
+        // src/masked/mask.rs:165-169, elided like a buffer: at most ten bits leave the device
+        use crate::Elided;
+        let n = self.len();
+        let (head, tail): (Vec<bool>, Vec<bool>) =
+            if n <= 10 { (self.to_vec(), Vec::new()) } else { ((0..5).map(|i| self.get(i)).collect(), (n - 5..n).map(|i| self.get(i)).collect()) };
+        f.write_str("Mask(")?;
+        if !head.is_empty() {
+            f.write_fmt(format_args!("{:?}", Elided(&head)))?;
+        }
+        if !tail.is_empty() {
+            f.write_str(", ... ")?;
+            f.write_fmt(format_args!("{:?}", Elided(&tail)))?;
+        }
+        f.write_str(")")
     }
 }
 impl Extend<bool> for Mask {
@@ -787,6 +854,26 @@ impl From<MaskedCellBuffer> for (CellBuffer, Mask) {
         (value.0, value.1)
     }
 }
+impl<'a> From<&'a MaskedCellBuffer> for (&'a CellBuffer, &'a Mask) {
+    fn from(value: &'a MaskedCellBuffer) -> Self {
+        (&value.0, &value.1) // src/masked/masked_buffer.rs:243-247
+    }
+}
+impl Debug for MaskedCellBuffer {
+    fn fmt(&self, f: &mut Formatter<'_>) -> std::fmt::Result {
+        // src/masked/masked_buffer.rs:227-235
+        let basename = self.cell_type().to_string();
+        f.debug_tuple(&format!("{basename}MaskedCellBuffer")).field(self.buffer()).field(self.mask()).finish()
+    }
+}
+impl<'buf> IntoIterator for &'buf MaskedCellBuffer {
+    type Item = (CellValue, bool);
+    type IntoIter = std::iter::Zip<std::vec::IntoIter<CellValue>, std::vec::IntoIter<bool>>;
+    fn into_iter(self) -> Self::IntoIter {
+        // src/masked/masked_buffer.rs:289-317 yields host pairs: one D2H copy of the cells, one of the unpacked mask
+        (&self.0).into_iter().zip(self.1.to_vec())
+    }
+}
 impl<C: CellEncoding> FromIterator<C> for MaskedCellBuffer {
     fn from_iter<I: IntoIterator<Item = C>>(iter: I) -> Self {
         // src/masked/masked_buffer.rs:257-261
@@ -927,6 +1014,12 @@ macro_rules! mcb_bin_op {
             type Output = MaskedCellBuffer;
             fn $mth(self, rhs: Self) -> MaskedCellBuffer {
                 $trt::$mth(&self, &rhs)
+            }
+        }
+        impl $trt<&MaskedCellBuffer> for MaskedCellBuffer {
+            type Output = MaskedCellBuffer;
+            fn $mth(self, rhs: &MaskedCellBuffer) -> MaskedCellBuffer {
+                $trt::$mth(&self, rhs) // :345-351
             }
         }
         impl<R: Into<CellValue>> $trt<R> for MaskedCellBuffer {
