@@ -455,9 +455,10 @@ class CellBuffer:
 
     def __repr__(self):
         """Debug (src/buffer.rs:188-203) with Elided (src/lib.rs:166-194)."""
-        v = self.to_vec()
-        items = [repr(x.item()) for x in (v if len(v) <= 10 else list(v[:5]) + list(v[-5:]))]
-        body = ", ".join(items) if len(v) <= 10 else ", ".join(items[:5]) + ", ... " + ", ".join(items[5:])
+        n = self.len()  # at most ten cells leave the device: a 4 GB raster in a pytest failure message must not be downloaded
+        v = self.to_vec() if n <= 10 else [self.get(i).value() for i in list(range(5)) + list(range(n - 5, n))]
+        items = [repr(x.item()) for x in v]
+        body = ", ".join(items) if n <= 10 else ", ".join(items[:5]) + ", ... " + ", ".join(items[5:])
         return f"{self.cell_type()}CellBuffer({body})"
 
 
@@ -572,8 +573,10 @@ class Mask:
     __hash__ = None
 
     def __repr__(self):
-        v = ["true" if b else "false" for b in self.to_vec()]
-        body = ", ".join(v) if len(v) <= 10 else ", ".join(v[:5]) + ", ... " + ", ".join(v[-5:])
+        n = self.len()
+        bits = self.to_vec() if n <= 10 else [self.get(i) for i in list(range(5)) + list(range(n - 5, n))]
+        v = ["true" if b else "false" for b in bits]
+        body = ", ".join(v) if n <= 10 else ", ".join(v[:5]) + ", ... " + ", ".join(v[5:])
         return f"Mask({body})"
 
 

@@ -62,6 +62,11 @@ def test_from_others():  # src/buffer.rs:528-556
 def test_debug():  # src/buffer.rs:558-564
     assert repr(CellBuffer.fill(5, CellValue.new(37))).startswith("Int32CellBuffer")
     assert "..." in repr(CellBuffer.fill(15, CellValue.new(37)))
+    # Elided (src/lib.rs:198-206): "1, 1, 1" and "0, 0, 0, 0, 0, ... 0, 0, 0, 0, 0"; only the ends leave the device
+    assert repr(CellBuffer.fill(3, CellValue(CellType.UInt8, 1))) == "UInt8CellBuffer(1, 1, 1)"
+    assert repr(CellBuffer.from_vec(np.arange(30, dtype=np.uint16))) == "UInt16CellBuffer(0, 1, 2, 3, 4, ... 25, 26, 27, 28, 29)"
+    assert repr(Mask.new([True, False] * 8)) == "Mask(true, false, true, false, true, ... false, true, false, true, false)"
+    assert repr(Mask.new([True, False, True])) == "Mask(true, false, true)"
 
 
 def test_convert():  # src/buffer.rs:566-578
