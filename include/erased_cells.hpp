@@ -245,16 +245,16 @@ public:
         detail::check(ec_buf_binary_scalar(op1, h_, o.h_, op2, &s.v, &h));
         return own(h);
     }
-    std::string debug() const {  // src/buffer.rs:188-203 + Elided
-        const std::vector<double> v = convert(CellType::Float64).to_vec<double>();
+    std::string debug() const {  // src/buffer.rs:188-203 + Elided: at most ten cells leave the device
+        const size_t n = len();
         std::string s = to_string(cell_type()) + "CellBuffer(";
-        auto item = [&](size_t i) { char b[64]; snprintf(b, sizeof b, "%g", v[i]); return std::string(b); };
-        if (v.size() > 10) {
+        auto item = [&](size_t i) { char b[64]; snprintf(b, sizeof b, "%g", get(i).to_f64().value_or(0.0)); return std::string(b); };
+        if (n > 10) {
             for (size_t i = 0; i < 5; ++i) s += item(i) + (i < 4 ? ", " : "");
             s += ", ... ";
-            for (size_t i = v.size() - 5; i < v.size(); ++i) s += item(i) + (i + 1 < v.size() ? ", " : "");
+            for (size_t i = n - 5; i < n; ++i) s += item(i) + (i + 1 < n ? ", " : "");
         } else {
-            for (size_t i = 0; i < v.size(); ++i) s += item(i) + (i + 1 < v.size() ? ", " : "");
+            for (size_t i = 0; i < n; ++i) s += item(i) + (i + 1 < n ? ", " : "");
         }
         return s + ")";
     }

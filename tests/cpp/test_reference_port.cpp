@@ -90,6 +90,8 @@ static void buffer_tests() {
     }
     CHECK(CellBuffer::fill(5, CellValue(37)).debug().rfind("Int32CellBuffer", 0) == 0);  // debug :558-564
     CHECK(CellBuffer::fill(15, CellValue(37)).debug().find("...") != std::string::npos);
+    CHECK(CellBuffer::from_vec(std::vector<uint16_t>{0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11}).debug() == "UInt16CellBuffer(0, 1, 2, 3, 4, ... 7, 8, 9, 10, 11)");
+    CHECK(CellBuffer::fill(3, CellValue(uint8_t(1))).debug() == "UInt8CellBuffer(1, 1, 1)");  // Elided, src/lib.rs:198-206
     for (CellType ct : cell_types()) {  // convert :566-578
         CellBuffer buf = CellBuffer::with_defaults(3, ct);
         for (CellType target : cell_types()) {
