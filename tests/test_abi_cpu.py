@@ -222,3 +222,18 @@ def test_rust_ffi_and_ctypes_bindings_match_the_header():
         for (ctype_c, pname), at in zip(args, argtypes):
             assert size_class(ctype_c) == py_class(at), (name, pname, ctype_c, at)
         assert (None if ret == "void" else size_class(ret)) == py_class(res), (name, ret, res)
+
+
+def test_every_environment_variable_is_documented():
+    """Each EC_* variable the library reads (env_int / getenv in csrc/) appears in INTEGRATION.md's table."""
+    import glob
+    import re
+
+    used = set()
+    for path in glob.glob(os.path.join(ROOT, "erased_cells_b200", "csrc", "*")):
+        if path.endswith((".cu", ".cuh", ".hpp", ".inc")):
+            used |= set(re.findall(r'(?:env_int|getenv)\("(EC_[A-Z_]+)"', open(path).read()))
+    assert len(used) >= 15, used
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = sorted(v for v in used if f"`{v}`" not in doc)
+    assert not missing, f"undocumented environment variables: {missing}"
